@@ -1,0 +1,174 @@
+/*
+ * mfar_b200.h - C ABI of the B200-native multi-field scoring + top-k retrieval path.
+ *
+ * The reference (microsoft/multifield-adaptive-retrieval) is pure Python and has no FFI of
+ * its own; the boundary this library replaces is the set of Python call sites listed next to
+ * each entry point (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller allocates every buffer; the library borrows, never frees;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and no entry
+ *     point synchronises (except the *_host convenience calls, which say so);
+ *   - return value: 0 = MFAR_OK, otherwise an mfar_status (mfar_status_string() names it);
+ *   - re-entrant, no global mutable state apart from a per-process cache of TMA descriptors'
+ *     driver entry point; one process per GPU;
+ *   - sm_100 only.  There is no CPU fallback: on any other device every compute entry point
+ *     returns MFAR_ERR_ARCH.
+ */
+#ifndef MFAR_B200_H_
+#define MFAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MFAR_ABI_VERSION 1
+#define MFAR_TILE_DOCS 128   /* docs per corpus tile (UMMA M)                       */
+#define MFAR_MAX_K 128       /* top-k depth limit (reference hard-codes k = 100)    */
+#define MFAR_MAX_FIELDS 64   /* dense + sparse fields (reference max: 44, PRIME)    */
+
+typedef enum mfar_status {
+  MFAR_OK = 0,
+  MFAR_ERR_ARG = 1,        /* null pointer / non-positive size / misaligned pointer  */
+  MFAR_ERR_SHAPE = 2,      /* dim, k, field count outside the supported envelope     */
+  MFAR_ERR_ARCH = 3,       /* current device is not compute capability 10.x          */
+  MFAR_ERR_WORKSPACE = 4,  /* workspace smaller than mfar_score_topk_workspace_bytes */
+  MFAR_ERR_CUDA = 5,       /* a CUDA runtime/driver call failed (see stderr)         */
+  MFAR_ERR_K_RANGE = 6     /* k > number of docs (reference: torch.topk raises)      */
+} mfar_status;
+
+typedef enum mfar_dtype { MFAR_F32 = 0, MFAR_BF16 = 1, MFAR_F16 = 2 } mfar_dtype;
+
+/* which scoring kernel mfar_score_topk runs */
+typedef enum mfar_impl {
+  MFAR_IMPL_AUTO = 0,   /* tcgen05 path whenever its shape constraints hold          */
+  MFAR_IMPL_SIMT = 1,   /* CUDA-core streaming path (small query batches, cross-check) */
+  MFAR_IMPL_TCGEN05 = 2 /* TMA + tcgen05.mma + TMEM path                              */
+} mfar_impl;
+
+int mfar_abi_version(void);
+const char* mfar_status_string(int status);
+/* 0 when `device` (or the current device if < 0) can run this library (sm_100). */
+int mfar_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Corpus store.  Replaces: the per-field headerless fp32 memmaps {temp_dir}/{field.name}.npy
+ * written at mfar/modeling/contrastive.py:482-490 and read at mfar/data/index.py:196,230
+ * (MemoryMapDict, mfar/data/util.py:28-59).
+ *
+ * Packed layout in HBM (bf16):  [n_tiles][n_fields][MFAR_TILE_DOCS][dim]
+ *   n_tiles = ceil(n_docs / 128); rows of the last tile beyond n_docs are zero.
+ * One (tile, field) block is 128*dim*2 contiguous bytes = one TMA box column.
+ * ------------------------------------------------------------------------------------------ */
+int64_t mfar_corpus_packed_elems(int64_t n_docs, int n_fields, int dim);
+
+/* Convert rows [row_begin, row_begin + n_rows) of ONE field from a row-major [n_rows, dim]
+ * slab (fp32 or bf16) into the packed corpus; optional per-row L2 normalisation (the
+ * reference's Normalize() module, mfar/modeling/util.py:50-51) before rounding to bf16.
+ * Call once per (field, slab); slabs may arrive in any order.  Zero the packed buffer first
+ * if n_docs is not a multiple of 128. */
+int mfar_corpus_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin,
+                          void* packed, int64_t n_docs, int n_fields, int field, int dim,
+                          int normalize, void* stream);
+
+/* Inverse view for tests / candidate export: copy rows of one field out as fp32 [n_rows, dim]. */
+int mfar_corpus_unpack_rows(const void* packed, int64_t n_docs, int n_fields, int field, int dim,
+                            int64_t row_begin, int64_t n_rows, float* dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Field mixture.  Replaces LinearWeights.forward, mfar/modeling/weighting.py:17-29, and the
+ * field mask of mfar/modeling/contrastive.py:686,706-714.
+ * ------------------------------------------------------------------------------------------ */
+/* out_w[q,f] = softmax_f(q_emb[q,:] @ W[:,f]) * mask[f]       (query_cond != 0, W is [E,F])
+ * out_w[q,f] = softmax_f(W[f,0]) * mask[f]                    (query_cond == 0, W is [F,1])
+ * mask may be NULL (all ones).  The mask multiplies AFTER the softmax: masked fields keep
+ * their softmax mass, weights are not renormalised - exactly contrastive.py:686 followed by
+ * weighting.py:28-29.  fp32 throughout. */
+int mfar_mixture_weights(const float* q_emb, const float* W, const float* mask, int Q, int E, int F,
+                         int query_cond, float* out_w, void* stream);
+
+/* out[b,s] = sum_f w[b or 0, f] * x[b,s,f]   (weighting.py:29).  w_rows is Q or 1. */
+int mfar_mixture_apply(const float* x, const float* w, int B, int S, int F, int w_rows, float* out,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused scoring + streaming top-k.  Replaces, in one pass over the corpus:
+ *   DenseFlatIndex.retrieve_batch   mfar/data/index.py:181-222   (q.V^T + running top-k)
+ *   DenseFlatIndex.score_batch      mfar/data/index.py:227-232   (subsumed: every doc is scored)
+ *   BM25sSparseIndex.score_batch    mfar/data/index.py:111-118   (gather of precomputed scores)
+ *   mask + LinearWeights + topk     mfar/modeling/contrastive.py:686,694,696
+ *
+ *   score[q,n] = sum_{f<n_dense} w[q,f] * <q_vec[q,:], corpus[n, field_begin+f, :]>
+ *              + sum_{j<n_sparse} w[q,n_dense+j] * sparse[q, j, n]
+ *   out = top-k over n of score[q,:], sorted by (score desc, doc id asc).
+ *
+ * corpus        packed bf16 corpus holding corpus_fields fields per tile; fields
+ *               [field_begin, field_begin+n_dense) are scored
+ * q_vecs        bf16 [Q, dim] row-major
+ * w             fp32 [Q, n_dense+n_sparse] (mask already folded in by mfar_mixture_weights)
+ * sparse        [Q, n_sparse, sparse_ld] fp32/f16 precomputed per-field scores of THIS shard's
+ *               docs (column n = local doc n); NULL when n_sparse == 0
+ * doc_id_base   added to the local doc index to form the emitted (global) doc id; ids must
+ *               stay below 2^32
+ * out_keys      optional uint64 [Q,k]: order-preserving (score,id) keys for mfar_topk_merge
+ * out_scores    fp32 [Q,k];  out_ids  int64 [Q,k];  slots beyond n_docs: (-inf, -1)
+ * ------------------------------------------------------------------------------------------ */
+size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse);
+
+int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
+                    int dim, const void* q_vecs, int Q, const float* w, const void* sparse, int n_sparse,
+                    int sparse_dtype, int64_t sparse_ld, int64_t doc_id_base, int k, uint64_t* out_keys,
+                    float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, int impl,
+                    void* stream);
+
+/* Merge L sorted-or-unsorted key lists per query into the global top-k.  Used for (a) the
+ * per-CTA partial lists inside mfar_score_topk and (b) the per-shard lists after the NCCL
+ * all-gather (replaces the {rank}.qres file merge of mfar/modeling/contrastive.py:616-631).
+ * keys: uint64 [L, Q, k_in]; key 0 = empty slot. */
+int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_t* out_keys,
+                    float* out_scores, int64_t* out_ids, void* stream);
+
+/* Reference quirk, mfar/data/index.py:192-193: the running top-k starts as k entries of
+ * (score 0.0, row 0).  Applies that to a finished [Q,k] result in place: entries scoring
+ * below 0.0 are replaced by (0.0, 0) and the list re-sorted. */
+int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Candidate re-scoring.  Replaces DenseFlatIndex.score_batch (mfar/data/index.py:227-232) and
+ * BM25sSparseIndex.score_batch's gather (index.py:116-117) for the union_rescore mode of
+ * trec_eval_step (contrastive.py:681-683).
+ *   out[f, q, c] = <q_vec[q], corpus[rows[c], field_begin+f]>      rows[c] < 0 -> 0
+ * ------------------------------------------------------------------------------------------ */
+int mfar_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin,
+                          int n_fields, int dim, const void* q_vecs, int Q, const int64_t* rows, int C,
+                          float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host-buffer convenience call (the end-to-end path a reference-side caller uses): copies the
+ * per-batch inputs host->device, runs mixture weights + mfar_score_topk on `stream`, copies the
+ * [Q,k] result back and synchronises the stream.  The corpus stays resident on the device.
+ * q_vecs_host: bf16 [Q,dim]; q_emb_host: fp32 [Q,E] (NULL if !query_cond); W/mask: DEVICE
+ * pointers (model state); sparse_host may be NULL.  scratch: device buffer of at least
+ * mfar_search_host_scratch_bytes(...) bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t mfar_search_host_scratch_bytes(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
+                                      int sparse_dtype, int k);
+
+int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
+                     int dim, const void* q_vecs_host, const float* q_emb_host, int Q, int E, const float* W,
+                     const float* mask, int query_cond, const void* sparse_host, int n_sparse,
+                     int sparse_dtype, int64_t doc_id_base, int k, float* out_scores_host,
+                     int64_t* out_ids_host, void* scratch, size_t scratch_bytes, int impl, void* stream);
+
+/* Number of kernels the last mfar_score_topk call on this thread launched (bench bookkeeping). */
+int mfar_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MFAR_B200_H_ */

@@ -1,0 +1,327 @@
+// Corpus pack/unpack, field-mixture weights, candidate re-scoring, sparse pre-mix and the
+// top-k merge.  All small / bandwidth-trivial next to the scoring pass; plain CUDA-core code.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mfar {
+
+// ---------------------------------------------------------------------------------------
+// pack: one warp per source row.  row-major [n_rows, dim] fp32|bf16 -> packed bf16
+// [tile][field][128][dim].  Optional L2 normalisation == torch.nn.functional.normalize
+// (x / max(||x||_2, 1e-12)), what sentence-transformers' Normalize() applies
+// (reference: mfar/modeling/util.py:50-51).
+// ---------------------------------------------------------------------------------------
+template <typename SrcT>
+__global__ void pack_rows_kernel(const SrcT* __restrict__ src, int64_t n_rows, int64_t row_begin,
+                                 __nv_bfloat16* __restrict__ packed, int n_fields, int field, int dim,
+                                 int normalize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const SrcT* s = src + r * dim;
+  float scale = 1.0f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+      float v = float(s[i]);
+      ss += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    scale = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  const int64_t doc = row_begin + r;
+  const int64_t tile = doc / kTileDocs;
+  const int in_tile = int(doc % kTileDocs);
+  __nv_bfloat16* d = packed + ((tile * n_fields + field) * kTileDocs + in_tile) * int64_t(dim);
+  for (int i = lane; i < dim; i += 32) d[i] = __float2bfloat16_rn(float(s[i]) * scale);
+}
+
+__global__ void unpack_rows_kernel(const __nv_bfloat16* __restrict__ packed, int n_fields, int field, int dim,
+                                   int64_t row_begin, int64_t n_rows, float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rows) return;
+  const int64_t doc = row_begin + r;
+  const __nv_bfloat16* s =
+      packed + (((doc / kTileDocs) * n_fields + field) * kTileDocs + (doc % kTileDocs)) * int64_t(dim);
+  for (int i = lane; i < dim; i += 32) dst[r * dim + i] = __bfloat162float(s[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// mixture weights: one CTA per query (or one CTA total when !query_cond).
+// logits[f] = sum_e q[e] * W[e*F + f];  w = softmax(logits) * mask.   weighting.py:25-28
+// ---------------------------------------------------------------------------------------
+__global__ void mixture_weights_kernel(const float* __restrict__ q_emb, const float* __restrict__ W,
+                                       const float* __restrict__ mask, int E, int F, int query_cond,
+                                       float* __restrict__ out_w) {
+  __shared__ float s_logit[MFAR_MAX_FIELDS];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  if (query_cond) {
+    const float* qe = q_emb + int64_t(q) * E;
+    for (int f = warp; f < F; f += nwarp) {
+      float acc = 0.f;
+      for (int e = lane; e < E; e += 32) acc = fmaf(qe[e], W[int64_t(e) * F + f], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) s_logit[f] = acc;
+    }
+  } else {
+    for (int f = threadIdx.x; f < F; f += blockDim.x) s_logit[f] = W[f];  // W is [F,1]
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float m = -INFINITY;
+    for (int f = lane; f < F; f += 32) m = fmaxf(m, s_logit[f]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int f = lane; f < F; f += 32) s += expf(s_logit[f] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int f = lane; f < F; f += 32) {
+      float w = expf(s_logit[f] - m) / s;
+      out_w[int64_t(q) * F + f] = mask ? w * mask[f] : w;
+    }
+  }
+}
+
+// out[b,s] = sum_f w[b or 0, f] * x[b,s,f]                                weighting.py:29
+__global__ void mixture_apply_kernel(const float* __restrict__ x, const float* __restrict__ w, int64_t BS,
+                                     int S, int F, int w_rows, float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= BS) return;
+  const int b = int(i / S);
+  const float* wr = w + (w_rows == 1 ? 0 : int64_t(b) * F);
+  const float* xr = x + i * F;
+  float acc = 0.f;
+  for (int f = 0; f < F; ++f) acc = fmaf(wr[f], xr[f], acc);
+  out[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// candidate re-scoring: one warp per (candidate, field); loops over queries.
+// out[f, q, c] = <q_vec[q], corpus[rows[c], field_begin + f]>;  rows[c] < 0 -> 0
+// ---------------------------------------------------------------------------------------
+__global__ void score_candidates_kernel(const __nv_bfloat16* __restrict__ corpus, int64_t n_docs, int corpus_fields,
+                                        int field_begin, int n_fields, int dim,
+                                        const __nv_bfloat16* __restrict__ q_vecs, int Q,
+                                        const int64_t* __restrict__ rows, int C, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= int64_t(C) * n_fields) return;
+  const int c = int(wid % C), f = int(wid / C);
+  const int64_t row = rows[c];
+  if (row < 0 || row >= n_docs) {
+    for (int q = lane; q < Q; q += 32) out[(int64_t(f) * Q + q) * C + c] = 0.f;
+    return;
+  }
+  const __nv_bfloat16* v =
+      corpus + (((row / kTileDocs) * corpus_fields + field_begin + f) * kTileDocs + (row % kTileDocs)) * int64_t(dim);
+  for (int q = 0; q < Q; ++q) {
+    const __nv_bfloat16* qv = q_vecs + int64_t(q) * dim;
+    float acc = 0.f;
+    for (int i = lane; i < dim; i += 32) acc = fmaf(__bfloat162float(qv[i]), __bfloat162float(v[i]), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[(int64_t(f) * Q + q) * C + c] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sparse pre-mix: base[q, n] = sum_j w[q, n_dense + j] * sparse[q, j, n]   (fp32)
+// Coalesced along n; 2 (f16) or 1 (f32) elements... kept simple: one thread per (q, 2 docs).
+// The scoring epilogue then gathers ONE value per (query, doc) instead of n_sparse.
+// ---------------------------------------------------------------------------------------
+template <typename ST>
+__global__ void sparse_premix_kernel(const ST* __restrict__ sparse, int64_t sparse_ld, int n_sparse,
+                                     const float* __restrict__ w, int w_ld, int w_off, int64_t n_docs,
+                                     float* __restrict__ base, int64_t base_ld) {
+  const int q = blockIdx.y;
+  const int64_t n = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= n_docs) return;
+  const float* wq = w + int64_t(q) * w_ld + w_off;
+  const ST* sp = sparse + int64_t(q) * n_sparse * sparse_ld + n;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < n_sparse; ++j) acc = fmaf(wq[j], float(sp[int64_t(j) * sparse_ld]), acc);
+  base[int64_t(q) * base_ld + n] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// merge: one CTA (512 threads) per query.  Streams every candidate key of that query from the
+// L lists through a 1024-slot shared buffer: admit keys >= running threshold, and whenever the
+// buffer may overflow bitonic-sort it, keep the best k, raise the threshold.
+// ---------------------------------------------------------------------------------------
+constexpr int kMergeThreads = 512;
+constexpr int kMergeBuf = 1024;
+
+__device__ __forceinline__ void block_sort1024_desc(uint64_t* buf) {
+  for (int s = 2; s <= kMergeBuf; s <<= 1) {
+    for (int d = s >> 1; d > 0; d >>= 1) {
+      __syncthreads();
+      const int t = threadIdx.x;                       // 512 compare-exchanges per stage
+      const int lo = ((t & ~(d - 1)) << 1) | (t & (d - 1));
+      const int hi = lo | d;
+      const bool desc = (lo & s) == 0 || s == kMergeBuf;
+      uint64_t a = buf[lo], b = buf[hi];
+      if ((a < b) == desc) { buf[lo] = b; buf[hi] = a; }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, const uint64_t* __restrict__ thr,
+             int L, int q_stride, int slots, int k, uint64_t* __restrict__ out_keys,
+             float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  __shared__ uint64_t buf[kMergeBuf];
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_thr;
+  const int q = blockIdx.x;
+  const int t = threadIdx.x;
+  if (t == 0) { s_cnt = 0; s_thr = 0ull; }
+  __syncthreads();
+  if (thr != nullptr) {                                // a list that was compacted holds >= k keys >= its thr
+    unsigned long long m = 0ull;
+    for (int l = t; l < L; l += kMergeThreads) {
+      unsigned long long v = thr[int64_t(l) * q_stride + q];
+      m = v > m ? v : m;
+    }
+    if (m) atomicMax(&s_thr, m);
+  }
+  __syncthreads();
+  const int64_t total = int64_t(L) * slots;
+  for (int64_t base = 0; base < total; base += kMergeThreads) {
+    const int64_t i = base + t;
+    if (i < total) {
+      const int l = int(i / slots), s = int(i % slots);
+      const int cnt = counts ? counts[int64_t(l) * q_stride + q] : slots;
+      if (s < cnt) {
+        const uint64_t key = keys[(int64_t(l) * q_stride + q) * slots + s];
+        if (key != 0ull && key >= s_thr) buf[atomicAdd(&s_cnt, 1)] = key;
+      }
+    }
+    __syncthreads();
+    const int c = s_cnt;                               // snapshot, then barrier: the branch below must be
+    __syncthreads();                                   // uniform even if fast threads start the next round
+    if (c > kMergeBuf - kMergeThreads) {
+      for (int j = c + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
+      block_sort1024_desc(buf);
+      if (t == 0) {
+        s_cnt = c < k ? c : k;
+        if (c >= k) s_thr = buf[k - 1];
+      }
+      __syncthreads();
+    }
+  }
+  const int c = s_cnt;
+  for (int j = c + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
+  block_sort1024_desc(buf);
+  for (int j = t; j < k; j += kMergeThreads) {
+    const uint64_t key = buf[j];
+    if (out_keys) out_keys[int64_t(q) * k + j] = key;
+    if (out_scores) out_scores[int64_t(q) * k + j] = key ? key_score(key) : -INFINITY;
+    if (out_ids) out_ids[int64_t(q) * k + j] = key ? int64_t(key_doc(key)) : int64_t(-1);
+  }
+}
+
+// index.py:192-193 quirk: running top-k starts as (0.0, row 0) entries.
+__global__ void zero_init_kernel(float* scores, int64_t* ids, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !(scores[i] >= 0.0f)) { scores[i] = 0.0f; ids[i] = 0; }
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+int launch_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin, void* packed,
+                     int n_fields, int field, int dim, int normalize, cudaStream_t st) {
+  if (n_rows == 0) return MFAR_OK;
+  const int threads = 256;
+  const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
+  if (src_dtype == MFAR_F32)
+    pack_rows_kernel<float><<<(unsigned)blocks, threads, 0, st>>>(static_cast<const float*>(src), n_rows, row_begin,
+                                                                 static_cast<__nv_bfloat16*>(packed), n_fields, field,
+                                                                 dim, normalize);
+  else if (src_dtype == MFAR_BF16)
+    pack_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(src), n_rows, row_begin, static_cast<__nv_bfloat16*>(packed), n_fields,
+        field, dim, normalize);
+  else
+    return MFAR_ERR_ARG;
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_unpack_rows(const void* packed, int n_fields, int field, int dim, int64_t row_begin, int64_t n_rows,
+                       float* dst, cudaStream_t st) {
+  if (n_rows == 0) return MFAR_OK;
+  const int threads = 256;
+  const int64_t blocks = (n_rows * 32 + threads - 1) / threads;
+  unpack_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(packed), n_fields, field,
+                                                           dim, row_begin, n_rows, dst);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_mixture_weights(const float* q_emb, const float* W, const float* mask, int Q, int E, int F,
+                           int query_cond, float* out_w, cudaStream_t st) {
+  mixture_weights_kernel<<<Q, 256, 0, st>>>(q_emb, W, mask, E, F, query_cond, out_w);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_mixture_apply(const float* x, const float* w, int B, int S, int F, int w_rows, float* out,
+                         cudaStream_t st) {
+  const int64_t BS = int64_t(B) * S;
+  if (BS == 0) return MFAR_OK;
+  mixture_apply_kernel<<<(unsigned)((BS + 255) / 256), 256, 0, st>>>(x, w, BS, S, F, w_rows, out);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_fields,
+                            int dim, const void* q_vecs, int Q, const int64_t* rows, int C, float* out,
+                            cudaStream_t st) {
+  if (C == 0 || n_fields == 0) return MFAR_OK;
+  const int64_t warps = int64_t(C) * n_fields;
+  score_candidates_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(corpus), n_docs, corpus_fields, field_begin, n_fields, dim,
+      static_cast<const __nv_bfloat16*>(q_vecs), Q, rows, C, out);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_sparse_premix(const void* sparse, int sparse_dtype, int64_t sparse_ld, int n_sparse, const float* w,
+                         int w_ld, int w_off, int Q, int64_t n_docs, float* base, int64_t base_ld,
+                         cudaStream_t st) {
+  dim3 grid((unsigned)((n_docs + 255) / 256), Q);
+  if (sparse_dtype == MFAR_F32)
+    sparse_premix_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(sparse), sparse_ld, n_sparse, w, w_ld,
+                                                      w_off, n_docs, base, base_ld);
+  else if (sparse_dtype == MFAR_F16)
+    sparse_premix_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(sparse), sparse_ld, n_sparse, w,
+                                                       w_ld, w_off, n_docs, base, base_ld);
+  else
+    return MFAR_ERR_ARG;
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
+                 int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  merge_kernel<<<Q, kMergeThreads, 0, st>>>(keys, counts, thr, L, q_stride, slots, k, out_keys, out_scores, out_ids);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_zero_init(float* scores, int64_t* ids, int n, cudaStream_t st) {
+  if (n == 0) return MFAR_OK;
+  zero_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(scores, ids, n);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+}  // namespace mfar

@@ -1,0 +1,278 @@
+// extern "C" entry points declared in include/mfar_b200.h.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace mfar;
+
+static thread_local int t_last_launches = 0;
+
+static int check_arch() {
+  static int cached = -1;   // one process per GPU
+  if (cached >= 0) return cached;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return MFAR_ERR_CUDA;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return MFAR_ERR_CUDA;
+  cached = (major == 10) ? MFAR_OK : MFAR_ERR_ARCH;
+  return cached;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Geometry {
+  int impl;       // resolved: MFAR_IMPL_SIMT or MFAR_IMPL_TCGEN05
+  int workers;
+  int q_tiles;
+  int q_pad;      // per tile (tc) or total (simt)
+  int q_pad_total;
+};
+
+static Geometry resolve_geometry(const ScoreArgs& a, int impl) {
+  Geometry g{};
+  if (impl == MFAR_IMPL_AUTO) impl = score_tc_supported(a) ? MFAR_IMPL_TCGEN05 : MFAR_IMPL_SIMT;
+  g.impl = impl;
+  if (impl == MFAR_IMPL_TCGEN05) {
+    score_tc_geometry(a.Q, a.n_tiles, &g.q_pad, &g.q_tiles, &g.workers);
+    g.q_pad_total = g.q_pad * g.q_tiles;
+  } else {
+    score_simt_geometry(a.Q, a.n_tiles, &g.q_pad, &g.workers);
+    g.q_tiles = 1;
+    g.q_pad_total = g.q_pad;
+  }
+  return g;
+}
+
+extern "C" {
+
+int mfar_abi_version(void) { return MFAR_ABI_VERSION; }
+
+const char* mfar_status_string(int status) {
+  switch (status) {
+    case MFAR_OK: return "ok";
+    case MFAR_ERR_ARG: return "invalid argument (null / non-positive / misaligned)";
+    case MFAR_ERR_SHAPE: return "shape outside the supported envelope";
+    case MFAR_ERR_ARCH: return "device is not sm_100 (no fallback path exists)";
+    case MFAR_ERR_WORKSPACE: return "workspace too small";
+    case MFAR_ERR_CUDA: return "CUDA call failed";
+    case MFAR_ERR_K_RANGE: return "k out of range";
+    default: return "unknown status";
+  }
+}
+
+int mfar_device_check(int device) {
+  int dev = device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) return MFAR_ERR_CUDA;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return MFAR_ERR_CUDA;
+  return major == 10 ? MFAR_OK : MFAR_ERR_ARCH;
+}
+
+int64_t mfar_corpus_packed_elems(int64_t n_docs, int n_fields, int dim) {
+  if (n_docs < 0 || n_fields <= 0 || dim <= 0) return -1;
+  const int64_t tiles = (n_docs + kTileDocs - 1) / kTileDocs;
+  return tiles * n_fields * kTileDocs * dim;
+}
+
+int mfar_corpus_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin, void* packed,
+                          int64_t n_docs, int n_fields, int field, int dim, int normalize, void* stream) {
+  if (!src || !packed || n_rows < 0 || row_begin < 0 || row_begin + n_rows > n_docs) return MFAR_ERR_ARG;
+  if (field < 0 || field >= n_fields || dim <= 0) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  return launch_pack_rows(src, src_dtype, n_rows, row_begin, packed, n_fields, field, dim, normalize,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int mfar_corpus_unpack_rows(const void* packed, int64_t n_docs, int n_fields, int field, int dim, int64_t row_begin,
+                            int64_t n_rows, float* dst, void* stream) {
+  if (!packed || !dst || n_rows < 0 || row_begin < 0 || row_begin + n_rows > n_docs) return MFAR_ERR_ARG;
+  if (field < 0 || field >= n_fields || dim <= 0) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  return launch_unpack_rows(packed, n_fields, field, dim, row_begin, n_rows, dst, static_cast<cudaStream_t>(stream));
+}
+
+int mfar_mixture_weights(const float* q_emb, const float* W, const float* mask, int Q, int E, int F, int query_cond,
+                         float* out_w, void* stream) {
+  if (!W || !out_w || Q <= 0 || (query_cond && (!q_emb || E <= 0))) return MFAR_ERR_ARG;
+  if (F <= 0 || F > MFAR_MAX_FIELDS) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  return launch_mixture_weights(q_emb, W, mask, Q, E, F, query_cond, out_w, static_cast<cudaStream_t>(stream));
+}
+
+int mfar_mixture_apply(const float* x, const float* w, int B, int S, int F, int w_rows, float* out, void* stream) {
+  if (!x || !w || !out || B <= 0 || S < 0) return MFAR_ERR_ARG;
+  if (F <= 0 || F > MFAR_MAX_FIELDS || (w_rows != 1 && w_rows != B)) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  return launch_mixture_apply(x, w, B, S, F, w_rows, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse) {
+  if (Q <= 0 || n_docs < 0) return 0;
+  (void)k;
+  const int n_tiles = int((n_docs + kTileDocs - 1) / kTileDocs);
+  size_t best = 0;
+  {
+    int qp, qt, w;
+    score_tc_geometry(Q, std::max(n_tiles, 1), &qp, &qt, &w);
+    best = std::max(best, topk_workspace_bytes(w, qp * qt));
+  }
+  {
+    int qp, w;
+    score_simt_geometry(Q, std::max(n_tiles, 1), &qp, &w);
+    best = std::max(best, topk_workspace_bytes(w, qp));
+  }
+  size_t total = align_up(best, 256);
+  if (n_sparse > 0) total += align_up(size_t(Q) * size_t(align_up(size_t(n_docs), 4)) * 4, 256);
+  return total;
+}
+
+int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
+                    const void* q_vecs, int Q, const float* w, const void* sparse, int n_sparse, int sparse_dtype,
+                    int64_t sparse_ld, int64_t doc_id_base, int k, uint64_t* out_keys, float* out_scores,
+                    int64_t* out_ids, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  t_last_launches = 0;
+  if (n_docs <= 0 || Q <= 0 || !w || !workspace || (!out_scores && !out_ids && !out_keys)) return MFAR_ERR_ARG;
+  if (n_dense < 0 || n_sparse < 0 || n_dense + n_sparse <= 0 || n_dense + n_sparse > MFAR_MAX_FIELDS)
+    return MFAR_ERR_SHAPE;
+  if (n_dense > 0 && (!corpus || !q_vecs || dim <= 0 || field_begin < 0 || field_begin + n_dense > corpus_fields))
+    return MFAR_ERR_ARG;
+  if (n_sparse > 0 && (!sparse || sparse_ld < n_docs)) return MFAR_ERR_ARG;
+  if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
+  if (doc_id_base < 0 || doc_id_base + n_docs > (int64_t(1) << 32)) return MFAR_ERR_SHAPE;
+  if (impl < MFAR_IMPL_AUTO || impl > MFAR_IMPL_TCGEN05) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  ScoreArgs a{};
+  a.corpus = corpus; a.n_docs = n_docs; a.n_tiles = int((n_docs + kTileDocs - 1) / kTileDocs);
+  a.corpus_fields = corpus_fields; a.field_begin = field_begin; a.n_dense = n_dense; a.dim = dim;
+  a.q_vecs = q_vecs; a.Q = Q; a.w = w; a.w_ld = n_dense + n_sparse; a.doc_id_base = doc_id_base; a.k = k;
+  if (impl == MFAR_IMPL_TCGEN05 && !score_tc_supported(a)) return MFAR_ERR_SHAPE;
+  const Geometry g = resolve_geometry(a, impl);
+
+  const size_t ws_topk = align_up(topk_workspace_bytes(g.workers, g.q_pad_total), 256);
+  const int64_t base_ld = int64_t(align_up(size_t(n_docs), 4));
+  const size_t ws_base = n_sparse > 0 ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
+  if (workspace_bytes < ws_topk + ws_base) return MFAR_ERR_WORKSPACE;
+  if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MFAR_ERR_ARG;
+
+  if (n_sparse > 0) {
+    float* base = reinterpret_cast<float*>(static_cast<char*>(workspace) + ws_topk);
+    if (int rc = launch_sparse_premix(sparse, sparse_dtype, sparse_ld, n_sparse, w, a.w_ld, n_dense, Q, n_docs, base,
+                                      base_ld, st))
+      return rc;
+    ++t_last_launches;
+    a.base = base;
+    a.base_ld = base_ld;
+  }
+  int rc;
+  if (g.impl == MFAR_IMPL_TCGEN05)
+    rc = launch_score_tc(a, workspace, g.workers, g.q_tiles, g.q_pad, st);
+  else
+    rc = launch_score_simt(a, workspace, g.workers, g.q_pad, st);
+  if (rc) return rc;
+  ++t_last_launches;
+  TopkWorkspace ws = carve_workspace(workspace, g.workers, g.q_pad_total);
+  rc = launch_merge(ws.cand_keys, ws.cand_cnt, ws.cand_thr, g.workers, g.q_pad_total, kCandCap, Q, k, out_keys,
+                    out_scores, out_ids, st);
+  if (rc) return rc;
+  ++t_last_launches;
+  return MFAR_OK;
+}
+
+int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_t* out_keys, float* out_scores,
+                    int64_t* out_ids, void* stream) {
+  if (!keys || L <= 0 || Q <= 0 || k_in <= 0) return MFAR_ERR_ARG;
+  if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  return launch_merge(keys, nullptr, nullptr, L, Q, k_in, Q, k, out_keys, out_scores, out_ids,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* stream) {
+  if (!scores || !ids || Q <= 0 || k <= 0) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  return launch_zero_init(scores, ids, Q * k, static_cast<cudaStream_t>(stream));
+}
+
+int mfar_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_fields,
+                          int dim, const void* q_vecs, int Q, const int64_t* rows, int C, float* out, void* stream) {
+  if (!corpus || !q_vecs || !rows || !out || Q <= 0 || C < 0 || n_docs <= 0) return MFAR_ERR_ARG;
+  if (n_fields <= 0 || field_begin < 0 || field_begin + n_fields > corpus_fields || dim <= 0) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  return launch_score_candidates(corpus, n_docs, corpus_fields, field_begin, n_fields, dim, q_vecs, Q, rows, C, out,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+// scratch layout for the host-buffer call
+struct HostScratch {
+  size_t off_q, off_qe, off_w, off_sparse, off_scores, off_ids, off_ws, total, ws_bytes;
+};
+static HostScratch host_scratch_layout(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
+                                       int sparse_dtype, int k) {
+  HostScratch h{};
+  size_t o = 0;
+  h.off_q = o;      o += align_up(size_t(Q) * dim * 2, 256);
+  h.off_qe = o;     o += align_up(size_t(Q) * std::max(E, 1) * 4, 256);
+  h.off_w = o;      o += align_up(size_t(Q) * (n_dense + n_sparse) * 4, 256);
+  h.off_sparse = o; o += align_up(size_t(Q) * n_sparse * size_t(n_docs) * (sparse_dtype == MFAR_F32 ? 4 : 2), 256);
+  h.off_scores = o; o += align_up(size_t(Q) * k * 4, 256);
+  h.off_ids = o;    o += align_up(size_t(Q) * k * 8, 256);
+  h.off_ws = o;
+  h.ws_bytes = mfar_score_topk_workspace_bytes(Q, k, n_docs, n_sparse);
+  h.total = o + h.ws_bytes;
+  return h;
+}
+
+size_t mfar_search_host_scratch_bytes(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
+                                      int sparse_dtype, int k) {
+  if (Q <= 0 || n_docs <= 0) return 0;
+  return host_scratch_layout(Q, dim, E, n_dense, n_sparse, n_docs, sparse_dtype, k).total;
+}
+
+int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
+                     const void* q_vecs_host, const float* q_emb_host, int Q, int E, const float* W, const float* mask,
+                     int query_cond, const void* sparse_host, int n_sparse, int sparse_dtype, int64_t doc_id_base,
+                     int k, float* out_scores_host, int64_t* out_ids_host, void* scratch, size_t scratch_bytes,
+                     int impl, void* stream) {
+  if (!scratch || !W || !out_scores_host || !out_ids_host || Q <= 0 || n_docs <= 0) return MFAR_ERR_ARG;
+  if (n_dense > 0 && !q_vecs_host) return MFAR_ERR_ARG;
+  if (query_cond && !q_emb_host) return MFAR_ERR_ARG;
+  if (n_sparse > 0 && !sparse_host) return MFAR_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(scratch) % 256 != 0) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  const HostScratch h = host_scratch_layout(Q, dim, E, n_dense, n_sparse, n_docs, sparse_dtype, k);
+  if (scratch_bytes < h.total) return MFAR_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* s = static_cast<char*>(scratch);
+  const int F = n_dense + n_sparse;
+  if (n_dense > 0)
+    MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_q, q_vecs_host, size_t(Q) * dim * 2, cudaMemcpyHostToDevice, st));
+  if (query_cond)
+    MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_qe, q_emb_host, size_t(Q) * E * 4, cudaMemcpyHostToDevice, st));
+  if (n_sparse > 0)
+    MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_sparse, sparse_host,
+                                 size_t(Q) * n_sparse * size_t(n_docs) * (sparse_dtype == MFAR_F32 ? 4 : 2),
+                                 cudaMemcpyHostToDevice, st));
+  float* w_dev = reinterpret_cast<float*>(s + h.off_w);
+  // query_cond == 0: the shared weight row is replicated per query so the scoring kernels index w[q, f] uniformly
+  if (int rc = launch_mixture_weights(query_cond ? reinterpret_cast<const float*>(s + h.off_qe) : nullptr, W, mask, Q,
+                                      E, F, query_cond, w_dev, st))
+    return rc;
+  float* sc = reinterpret_cast<float*>(s + h.off_scores);
+  int64_t* ids = reinterpret_cast<int64_t*>(s + h.off_ids);
+  int rc = mfar_score_topk(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, s + h.off_q, Q, w_dev,
+                           n_sparse ? s + h.off_sparse : nullptr, n_sparse, sparse_dtype, n_docs, doc_id_base, k,
+                           nullptr, sc, ids, s + h.off_ws, h.ws_bytes, impl, st);
+  if (rc) return rc;
+  t_last_launches += 1;
+  MFAR_CUDA_OK(cudaMemcpyAsync(out_scores_host, sc, size_t(Q) * k * 4, cudaMemcpyDeviceToHost, st));
+  MFAR_CUDA_OK(cudaMemcpyAsync(out_ids_host, ids, size_t(Q) * k * 8, cudaMemcpyDeviceToHost, st));
+  MFAR_CUDA_OK(cudaStreamSynchronize(st));
+  return MFAR_OK;
+}
+
+int mfar_last_launch_count(void) { return t_last_launches; }
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+// Shared device/host helpers for the mFAR B200 scoring path.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mfar_b200.h"
+
+namespace mfar {
+
+constexpr int kTileDocs = MFAR_TILE_DOCS;  // docs per corpus tile == UMMA M
+constexpr int kMaxK = MFAR_MAX_K;
+constexpr int kCandCap = 256;              // per-(worker, query) candidate slots; >= kMaxK + kTileDocs
+constexpr int kNumSmsB200 = 148;
+
+#define MFAR_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      fprintf(stderr, "[mfar_b200] %s failed: %s (%s:%d)\n", #expr, cudaGetErrorString(_e),  \
+              __FILE__, __LINE__);                                                           \
+      return MFAR_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// (score, doc id) <-> order-preserving 64-bit key.
+//   high 32 bits: float score mapped so that unsigned order == float order
+//   low  32 bits: ~doc_id, so that among equal scores the LOWER doc id is the LARGER key
+// max-key-first order therefore is (score desc, doc id asc): the deterministic tie-break the
+// oracle's topk_sorted() uses.  Key 0 is never produced by a finite score: it marks "empty".
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t doc_id) {
+  return (uint64_t(float_to_ordered(score)) << 32) | uint64_t(~doc_id);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) { return ordered_to_float(uint32_t(key >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_doc(uint64_t key) { return ~uint32_t(key & 0xFFFFFFFFull); }
+
+// Workspace carve-up shared by the scoring kernels and the merge.
+//   cand_keys [G][Qp][kCandCap] u64 | cand_cnt [G][Qp] i32 | cand_thr [G][Qp] u64 | err flag
+struct TopkWorkspace {
+  uint64_t* cand_keys;
+  int* cand_cnt;
+  uint64_t* cand_thr;
+  int* err;
+  int workers;  // G
+  int q_pad;    // Qp
+};
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline size_t topk_workspace_bytes(int workers, int q_pad) {
+  size_t n = size_t(workers) * q_pad;
+  return n * kCandCap * 8 + n * 8 + n * 4 + 256;
+}
+inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
+  TopkWorkspace w;
+  size_t n = size_t(workers) * q_pad;
+  char* p = static_cast<char*>(base);
+  w.cand_keys = reinterpret_cast<uint64_t*>(p); p += n * kCandCap * 8;
+  w.cand_thr = reinterpret_cast<uint64_t*>(p);  p += n * 8;
+  w.cand_cnt = reinterpret_cast<int*>(p);       p += n * 4;
+  w.err = reinterpret_cast<int*>(p);
+  w.workers = workers;
+  w.q_pad = q_pad;
+  return w;
+}
+
+// --------------------------------------------------------------------------------------
+// Warp-level bitonic sort, descending, of 256 u64 keys held 8 per lane (element e = lane*8+j).
+// Compare distances 1,2,4 stay inside a lane; 8..128 are one 64-bit shuffle each.
+// --------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_sort256_desc(uint64_t (&v)[8], int lane) {
+#pragma unroll
+  for (int s = 2; s <= 256; s <<= 1) {
+#pragma unroll
+    for (int d = s >> 1; d > 0; d >>= 1) {
+      if (d >= 8) {
+        const int lane_d = d >> 3;
+        const bool upper = (lane & lane_d) != 0;              // this lane holds the higher index of the pair
+        const bool desc = ((lane * 8) & s) == 0 || s == 256;  // block direction (same for all 8 elems: s > 8)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint64_t o = __shfl_xor_sync(0xffffffffu, v[j], lane_d);
+          uint64_t mx = v[j] > o ? v[j] : o, mn = v[j] > o ? o : v[j];
+          v[j] = (desc != upper) ? mx : mn;                   // lower index keeps max when descending
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((j & d) == 0) {
+            const int e = lane * 8 + j;
+            const bool desc = ((e & s) == 0) || s == 256;
+            uint64_t a = v[j], b = v[j | d];
+            uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
+            v[j] = desc ? mx : mn;
+            v[j | d] = desc ? mn : mx;
+          }
+        }
+      }
+    }
+  }
+}
+
+// One warp compacts the candidate list of one (worker, query): keep the best k keys (sorted
+// descending), return the k-th key (new admission threshold).  `list` points at kCandCap slots
+// in global memory written earlier by threads of this CTA (made visible by a CTA barrier).
+__device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, int count, int k, int lane) {
+  uint64_t v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int e = lane * 8 + j;
+    v[j] = (e < count) ? __ldcg(list + e) : 0ull;
+  }
+  warp_sort256_desc(v, lane);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int e = lane * 8 + j;
+    if (e < k) __stcg(list + e, v[j]);
+  }
+  // k-th key lives in lane (k-1)/8, register (k-1)%8
+  uint64_t kth = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (((k - 1) & 7) == j) kth = v[j];
+  return __shfl_sync(0xffffffffu, kth, (k - 1) >> 3);
+}
+
+}  // namespace mfar

@@ -1,0 +1,55 @@
+// Internal launcher declarations (host side).  Each returns an mfar_status.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mfar {
+
+int launch_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin, void* packed,
+                     int n_fields, int field, int dim, int normalize, cudaStream_t st);
+int launch_unpack_rows(const void* packed, int n_fields, int field, int dim, int64_t row_begin, int64_t n_rows,
+                       float* dst, cudaStream_t st);
+int launch_mixture_weights(const float* q_emb, const float* W, const float* mask, int Q, int E, int F,
+                           int query_cond, float* out_w, cudaStream_t st);
+int launch_mixture_apply(const float* x, const float* w, int B, int S, int F, int w_rows, float* out,
+                         cudaStream_t st);
+int launch_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_fields,
+                            int dim, const void* q_vecs, int Q, const int64_t* rows, int C, float* out,
+                            cudaStream_t st);
+int launch_sparse_premix(const void* sparse, int sparse_dtype, int64_t sparse_ld, int n_sparse, const float* w,
+                         int w_ld, int w_off, int Q, int64_t n_docs, float* base, int64_t base_ld,
+                         cudaStream_t st);
+int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
+                 int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
+int launch_zero_init(float* scores, int64_t* ids, int n, cudaStream_t st);
+
+// Arguments common to both scoring kernels (all device pointers).
+struct ScoreArgs {
+  const void* corpus;       // packed bf16 [tiles][corpus_fields][128][dim]
+  int64_t n_docs;
+  int n_tiles;
+  int corpus_fields;
+  int field_begin;
+  int n_dense;
+  int dim;
+  const void* q_vecs;       // bf16 [Q, dim]
+  int Q;
+  const float* w;           // fp32 [Q, w_ld]
+  int w_ld;
+  const float* base;        // fp32 [Q, base_ld] pre-mixed sparse contribution or nullptr
+  int64_t base_ld;
+  int64_t doc_id_base;
+  int k;
+};
+
+// SIMT (CUDA-core) scoring pass.  workers = grid size; fills ws candidate lists.
+int launch_score_simt(const ScoreArgs& a, void* ws_base, int workers, int q_pad, cudaStream_t st);
+// TMA + tcgen05 scoring pass.
+int launch_score_tc(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int q_pad, cudaStream_t st);
+// Shape envelope of the tcgen05 path.
+bool score_tc_supported(const ScoreArgs& a);
+// geometry chosen for (Q): q_pad per tile, number of q tiles, workers
+void score_tc_geometry(int Q, int n_tiles, int* q_pad, int* q_tiles, int* workers);
+void score_simt_geometry(int Q, int n_tiles, int* q_pad, int* workers);
+
+}  // namespace mfar

@@ -1,0 +1,415 @@
+// Fused multi-field scoring + streaming top-k on the 5th-gen tensor cores (sm_100a).
+//
+//   score[q, n] = sum_f w[q,f] * <q_vec[q], corpus[n, f, :]>  (+ base[q, n])  ->  per-CTA top-k
+//
+// Work decomposition
+//   corpus tile  = 128 docs (UMMA M = 128, one TMEM lane per doc)
+//   unit         = (tile, field): D_f[128 docs x QP queries] = A[128 x dim] . B[QP x dim]^T
+//   A            = the (tile, field) block of the packed corpus, contiguous 128*dim bf16 in HBM,
+//                  streamed by TMA in K-chunks of 64 (16 KB, SWIZZLE_128B) through a ring of stages
+//   B            = the CTA's query tile (QP <= 64 rows), TMA-loaded ONCE and resident in shared
+//                  memory for the whole kernel (QP*dim*2 B)
+//   D            = fp32 accumulators in TMEM, double buffered (2 x QP columns)
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..5  epilogue: tcgen05.ld the finished D_f, acc[q] += w[q,f] * D_f[doc,q] in registers
+//               (fp32 weights applied AFTER the fp32 accumulation - never folded into bf16 operands),
+//               and after the last field: + pre-mixed sparse term, threshold filter, candidate push,
+//               warp-level list compaction.  No [Q x N x F] (or [Q x N]) score tensor is ever written.
+//
+// grid = (workers, q_tiles): CTAs with the same blockIdx.x walk the same tile sequence for different
+// query tiles, so a corpus tile is fetched from HBM once and re-read from L2 by the other q-tiles.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mfar {
+
+constexpr int kTcThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kChunkK = 64;                       // bf16 elements per K-chunk = 128 B = swizzle span
+constexpr int kABytes = kTileDocs * kChunkK * 2;  // 16 KB per stage
+constexpr int kUmmaK = 16;
+constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;  // ~2 s: turn a pipeline bug into a trap, not a hang
+
+struct TcParams {
+  int64_t n_docs;
+  int n_tiles, corpus_fields, field_begin, n_dense, k_chunks;
+  int Q;
+  const float* w;
+  int w_ld;
+  const float* base;
+  int64_t base_ld;
+  int64_t doc_id_base;
+  int k;
+  int stages;
+  TopkWorkspace ws;
+};
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > kWaitTimeoutCycles) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major: 1) | [32,46) SBO >> 4
+//   (8 rows * 128 B = 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+// QP: query columns per CTA (UMMA N), one of 16 / 32 / 64.
+template <int QP>
+__global__ void __launch_bounds__(kTcThreads, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B resident][w_s][thr][cnt][barriers][tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + size_t(p.stages) * kABytes;
+  const int b_chunk_bytes = QP * kChunkK * 2;
+  float* w_s = reinterpret_cast<float*>(smem_b + size_t(p.k_chunks) * b_chunk_bytes);     // [n_dense][QP]
+  unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(w_s + size_t(p.n_dense) * QP);
+  int* s_cnt = reinterpret_cast<int*>(s_thr + QP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_cnt + QP) + 7) & ~uintptr_t(7));
+  uint64_t* full_bar = bars;                       // [stages]
+  uint64_t* empty_bar = bars + p.stages;           // [stages]
+  uint64_t* tfull_bar = bars + 2 * p.stages;       // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint64_t* bq_bar = tempty_bar + 2;               // [1]
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bq_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x;                        // worker (walks tiles g, g+G, ...)
+  const int q0 = blockIdx.y * QP;                  // first query of this CTA's tile
+  const int nq = min(QP, p.Q - q0);
+  int* err = p.ws.err;
+  constexpr uint32_t kTmemCols = (2 * QP < 32) ? 32 : 2 * QP;
+
+  // ---- one-time setup
+  for (int i = threadIdx.x; i < p.n_dense * QP; i += kTcThreads) {
+    const int f = i / QP, c = i % QP;
+    w_s[i] = (c < nq) ? p.w[int64_t(q0 + c) * p.w_ld + f] : 0.f;
+  }
+  if (threadIdx.x < QP) { s_thr[threadIdx.x] = 0ull; s_cnt[threadIdx.x] = 0; }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiThreads); }
+    mbar_init(bq_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_s, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const int my_tiles = (p.n_tiles > g) ? (p.n_tiles - g + gridDim.x - 1) / gridDim.x : 0;
+  const int units = my_tiles * p.n_dense;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0 && units > 0) {
+      mbar_expect_tx(bq_bar, uint32_t(p.k_chunks) * b_chunk_bytes);
+      for (int kc = 0; kc < p.k_chunks; ++kc)
+        tma_load_2d(&map_b, bq_bar, smem_b + size_t(kc) * b_chunk_bytes, kc * kChunkK, q0);
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int t = g + i * gridDim.x;
+        for (int f = 0; f < p.n_dense; ++f) {
+          const int row0 = (t * p.corpus_fields + p.field_begin + f) * kTileDocs;
+          for (int kc = 0; kc < p.k_chunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, err, 1);
+            mbar_expect_tx(&full_bar[stage], kABytes);
+            tma_load_2d(&map_a, &full_bar[stage], smem_a + size_t(stage) * kABytes, kc * kChunkK, row0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0 && units > 0) {
+      constexpr uint32_t idesc = make_idesc(kTileDocs, QP);
+      mbar_wait(bq_bar, 0, err, 2);
+      tc_fence_after();
+      int stage = 0; uint32_t phase = 0;
+      for (int u = 0; u < units; ++u) {
+        const int buf = u & 1;
+        mbar_wait(&tempty_bar[buf], ((u >> 1) & 1) ^ 1, err, 3);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(buf * QP);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase, err, 4);
+          tc_fence_after();
+          const uint64_t a_desc = make_sw128_desc(smem_u32(smem_a + size_t(stage) * kABytes));
+          const uint64_t b_desc = make_sw128_desc(smem_u32(smem_b + size_t(kc) * b_chunk_bytes));
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / kUmmaK; ++kk) {
+            // advance 16 elements = 32 B along K inside the 128 B swizzle span: +2 in the >>4 address field
+            umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+          }
+          tc_commit(&empty_bar[stage]);            // smem stage reusable once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[buf]);                // accumulator of this unit complete
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int lane_grp = warp & 3;                 // TMEM lanes 32*lane_grp .. +31 are this warp's
+    const int doc_in_tile = lane_grp * 32 + lane;
+    const int epi_warp = warp - 2;
+    float acc[QP];
+    int u = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int t = g + i * gridDim.x;
+#pragma unroll
+      for (int c = 0; c < QP; ++c) acc[c] = 0.f;
+      for (int f = 0; f < p.n_dense; ++f, ++u) {
+        const int buf = u & 1;
+        mbar_wait(&tfull_bar[buf], (u >> 1) & 1, err, 5);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(buf * QP);
+        const float* wf = w_s + f * QP;
+#pragma unroll
+        for (int c0 = 0; c0 < QP; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wf + c0 + c);
+            acc[c0 + c + 0] = fmaf(w4.x, __uint_as_float(v[c + 0]), acc[c0 + c + 0]);
+            acc[c0 + c + 1] = fmaf(w4.y, __uint_as_float(v[c + 1]), acc[c0 + c + 1]);
+            acc[c0 + c + 2] = fmaf(w4.z, __uint_as_float(v[c + 2]), acc[c0 + c + 2]);
+            acc[c0 + c + 3] = fmaf(w4.w, __uint_as_float(v[c + 3]), acc[c0 + c + 3]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);             // 128 arrivals free the accumulator buffer
+      }
+      // ---- tile done: add pre-mixed sparse term, filter, push
+      const int64_t doc_local = int64_t(t) * kTileDocs + doc_in_tile;
+      if (doc_local < p.n_docs) {
+        const uint32_t doc_id = uint32_t(p.doc_id_base + doc_local);
+#pragma unroll
+        for (int c = 0; c < QP; ++c) {
+          if (c < nq) {
+            float s = acc[c];
+            if (p.base) s += __ldg(p.base + int64_t(q0 + c) * p.base_ld + doc_local);
+            const uint64_t key = make_key(s, doc_id);
+            if (key > s_thr[c]) {
+              const int pos = atomicAdd(&s_cnt[c], 1);
+              __stcg(p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap + pos, key);
+            }
+          }
+        }
+      }
+      epi_bar_sync();
+      for (int c = epi_warp; c < nq; c += kEpiThreads / 32) {
+        const int cnt = s_cnt[c];
+        if (cnt > kCandCap - kTileDocs) {
+          uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
+          const uint64_t kth = warp_compact_list(list, cnt, p.k, lane);
+          if (lane == 0) { s_thr[c] = kth; s_cnt[c] = p.k; }
+        }
+      }
+      epi_bar_sync();
+    }
+    const int et = threadIdx.x - 64;
+    if (et < nq) {
+      p.ws.cand_cnt[int64_t(g) * p.ws.q_pad + q0 + et] = s_cnt[et];
+      p.ws.cand_thr[int64_t(g) * p.ws.q_pad + q0 + et] = s_thr[et];
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128-byte swizzle.
+static int make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       CUtensorMapL2promotion promo) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MFAR_ERR_CUDA;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {kChunkK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[mfar_b200] cuTensorMapEncodeTiled failed: %d\n", int(r));
+    return MFAR_ERR_CUDA;
+  }
+  return MFAR_OK;
+}
+
+bool score_tc_supported(const ScoreArgs& a) {
+  return a.n_dense >= 1 && a.dim % kChunkK == 0 && a.dim >= kChunkK && a.dim <= 1024 &&
+         (reinterpret_cast<uintptr_t>(a.corpus) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.q_vecs) % 16 == 0) &&
+         int64_t(a.n_tiles) * a.corpus_fields * kTileDocs < (int64_t(1) << 31);
+}
+
+void score_tc_geometry(int Q, int n_tiles, int* q_pad, int* q_tiles, int* workers) {
+  int qp = Q <= 16 ? 16 : (Q <= 32 ? 32 : 64);
+  int qt = (Q + qp - 1) / qp;
+  int w = kNumSmsB200 / qt;
+  if (w < 1) w = 1;
+  if (w > n_tiles) w = n_tiles;
+  if (w < 1) w = 1;
+  *q_pad = qp; *q_tiles = qt; *workers = w;
+}
+
+static size_t tc_smem_bytes(int qp, int n_dense, int k_chunks, int stages) {
+  return 1024 + size_t(stages) * kABytes + size_t(k_chunks) * qp * kChunkK * 2 + size_t(n_dense) * qp * 4 +
+         size_t(qp) * 12 + 8 + (2 * stages + 5) * 8 + 16;
+}
+
+template <int QP>
+static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, cudaStream_t st) {
+  TcParams p;
+  p.n_docs = a.n_docs; p.n_tiles = a.n_tiles; p.corpus_fields = a.corpus_fields; p.field_begin = a.field_begin;
+  p.n_dense = a.n_dense; p.k_chunks = a.dim / kChunkK; p.Q = a.Q; p.w = a.w; p.w_ld = a.w_ld; p.base = a.base;
+  p.base_ld = a.base_ld; p.doc_id_base = a.doc_id_base; p.k = a.k;
+  p.ws = carve_workspace(ws_base, workers, q_tiles * QP);
+  int stages = 8;
+  const size_t smem_cap = 227 * 1024;
+  while (stages > 2 && tc_smem_bytes(QP, a.n_dense, p.k_chunks, stages) > smem_cap) --stages;
+  if (tc_smem_bytes(QP, a.n_dense, p.k_chunks, stages) > smem_cap) return MFAR_ERR_SHAPE;
+  p.stages = stages;
+  const size_t smem = tc_smem_bytes(QP, a.n_dense, p.k_chunks, stages);
+
+  CUtensorMap map_a, map_b;
+  int rc = make_map_2d(&map_a, a.corpus, uint64_t(a.n_tiles) * a.corpus_fields * kTileDocs, a.dim, kTileDocs,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc) return rc;
+  rc = make_map_2d(&map_b, a.q_vecs, uint64_t(a.Q), a.dim, QP, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  if (rc) return rc;
+
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    MFAR_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+    attr_set = true;
+  }
+  dim3 grid(workers, q_tiles);
+  score_tc_kernel<QP><<<grid, kTcThreads, smem, st>>>(map_a, map_b, p);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_score_tc(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int q_pad, cudaStream_t st) {
+  if (!score_tc_supported(a)) return MFAR_ERR_SHAPE;
+  switch (q_pad) {
+    case 16: return launch_tc_impl<16>(a, ws_base, workers, q_tiles, st);
+    case 32: return launch_tc_impl<32>(a, ws_base, workers, q_tiles, st);
+    case 64: return launch_tc_impl<64>(a, ws_base, workers, q_tiles, st);
+    default: return MFAR_ERR_SHAPE;
+  }
+}
+
+}  // namespace mfar

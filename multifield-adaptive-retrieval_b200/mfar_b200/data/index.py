@@ -1,0 +1,143 @@
+"""Index API of the scoring path (mfar/data/index.py).
+
+``Index``                  - the ABC (index.py:21-37)
+``DenseFlatIndex``         - exhaustive flat dense index over ONE field (index.py:160-232); same
+                             constructor and return types, every dot product / top-k on the GPU
+``PrecomputedSparseIndex`` - stands where ``BM25sSparseIndex`` stands (index.py:39-157) for this
+                             path: BM25 arithmetic (third-party bm25s) is out of scope, the index
+                             serves PRECOMPUTED per-query full-corpus score vectors and does the
+                             gather / top-k the reference does around them (index.py:95-118)
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from typing import Dict, Generic, List, Optional, Sequence, Tuple, TypeVar, Union
+
+import numpy as np
+import torch
+
+from .. import _native as nv
+
+Key = TypeVar("Key")
+Query = TypeVar("Query")
+
+
+class Index(ABC, Generic[Key, Query]):
+    """Anything that can be searched (index.py:21-37)."""
+
+    @abstractmethod
+    def retrieve(self, query: Query, top_k: int) -> Sequence[Tuple[Key, float]]:
+        raise NotImplementedError
+
+    def retrieve_batch(self, queries: Sequence[Query], top_k: int) -> Sequence[Sequence[Tuple[Key, float]]]:
+        return [self.retrieve(q, top_k) for q in queries]
+
+
+class DenseFlatIndex(Index[str, str]):
+    """Flat exhaustive index over one dense field.
+
+    ``vectors`` is the field's [N, d] fp32 array (the reference passes ``MemoryMapDict.file``,
+    mfar/modeling/util.py:96-101).  It is packed to bf16 on the device lazily and re-packed when
+    ``.vectors`` is rebound (the reference rebinds it after the corpus is encoded,
+    contrastive.py:493-494).  ``device`` must be a CUDA device; ``vector_batch_size`` is accepted
+    for signature compatibility (the fused kernel streams the whole field in one pass)."""
+
+    def __init__(self, model, vectors, numeric_ids_to_keys: Sequence[str], keys_to_numeric_ids: Dict[str, int],
+                 device: Union[str, torch.device] = "cuda", vector_batch_size: int = 1048576,
+                 normalize: bool = False):
+        self.model = model
+        self._vectors = vectors
+        self.numeric_ids_to_key = numeric_ids_to_keys
+        self.key_to_numeric_ids = keys_to_numeric_ids
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("DenseFlatIndex (mfar_b200) runs on a CUDA sm_100 device only; no CPU path")
+        self.vector_batch_size = vector_batch_size
+        self.normalize = normalize
+        self._retriever = None
+
+    # rebinding .vectors invalidates the packed copy (contrastive.py:493-494)
+    @property
+    def vectors(self):
+        return self._vectors
+
+    @vectors.setter
+    def vectors(self, value) -> None:
+        self._vectors = value
+        self._retriever = None
+
+    def _ensure(self):
+        if self._retriever is None:
+            from ..modeling.retrieval import MultiFieldRetriever, PackedCorpus
+            from ..modeling.weighting import LinearWeights
+            pc = PackedCorpus.from_fields([self._vectors], self.device, self.normalize)
+            mix = LinearWeights(1, 1).to(self.device)          # single field: weight softmax == 1
+            self._retriever = MultiFieldRetriever(pc, mix, top_k=100)
+        return self._retriever
+
+    def _encode(self, queries) -> torch.Tensor:
+        if isinstance(queries, np.ndarray):                    # index.py:184-185
+            return torch.from_numpy(queries)
+        if torch.is_tensor(queries):
+            return queries
+        return self.model.encode(list(queries), convert_to_tensor=True)   # index.py:187
+
+    def retrieve(self, query, top_k: int):
+        return self.retrieve_batch([query], top_k)[0]
+
+    def retrieve_batch(self, queries, top_k: int) -> List[List[Tuple[str, float]]]:
+        r = self._ensure()
+        s, i = r.per_field_topk(self._encode(queries), None, top_k, zero_init=True)
+        rows, vals = i[0].cpu().tolist(), s[0].cpu().tolist()
+        return [list(zip([self.numeric_ids_to_key[j] for j in rows[q]], vals[q])) for q in range(len(rows))]
+
+    def score(self, query, keys: Sequence[str]) -> torch.Tensor:
+        return self.score_batch([query], keys)[0]
+
+    def score_batch(self, queries, keys: Sequence[str]) -> torch.Tensor:
+        """[Q, C] fp32 scores of the given keys (index.py:227-232); unknown key -> KeyError, as there."""
+        r = self._ensure()
+        rows = torch.tensor([self.key_to_numeric_ids[k] for k in keys], dtype=torch.int64)
+        return r.score_candidates(self._encode(queries), rows)[0]
+
+
+class PrecomputedSparseIndex(Index[str, str]):
+    """Sparse field index fed with precomputed score vectors.
+
+    ``scores`` maps a query (text or id) to its full-corpus fp32/fp16 score vector [N] - what
+    ``BM25sSparseIndex.get_scores`` returns (index.py:72-76)."""
+
+    def __init__(self, keys: List[str], scores: Dict[str, "np.ndarray"], device: Union[str, torch.device] = "cuda"):
+        self.keys = keys
+        self.key_to_id = {key: i for i, key in enumerate(keys)}
+        self.scores = scores
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PrecomputedSparseIndex (mfar_b200) runs on a CUDA sm_100 device only")
+        self.name = None
+
+    def get_scores(self, query) -> np.ndarray:
+        return self.scores[query]
+
+    def _stack(self, queries) -> torch.Tensor:
+        return torch.from_numpy(np.stack([np.asarray(self.scores[q]) for q in queries])).to(self.device)
+
+    def retrieve(self, query, top_k: int):
+        return self.retrieve_batch([query], top_k)[0]
+
+    def retrieve_batch(self, queries, top_k: int):
+        from ..modeling.retrieval import MultiFieldRetriever
+        from ..modeling.weighting import LinearWeights
+        sv = self._stack(queries)                                                    # [Q,N]
+        r = MultiFieldRetriever(None, LinearWeights(1, 1).to(self.device), n_sparse=1, top_k=top_k,
+                                n_docs=sv.shape[1], device=self.device)
+        s, i = r.per_field_topk(None, sv.unsqueeze(1), top_k, zero_init=False)
+        rows, vals = i[0].cpu().tolist(), s[0].cpu().tolist()
+        return [[(self.keys[j], v) for j, v in zip(rows[q], vals[q])] for q in range(len(rows))]
+
+    def score_batch(self, queries, keys: Sequence[str]) -> torch.Tensor:
+        """[Q, C]; keys missing from the index score 0 (index.py:112-117)."""
+        rows = torch.tensor([self.key_to_id.get(k, -1) for k in keys], dtype=torch.int64, device=self.device)
+        sv = self._stack(queries).float()
+        out = sv[:, rows.clamp(min=0)]
+        return out * (rows >= 0).to(out.dtype)

@@ -1,0 +1,350 @@
+"""Multi-field retrieval over the packed corpus: the B200 replacement of
+``RetrievalTrainingModule.trec_eval_step`` / ``mask_field`` (mfar/modeling/contrastive.py:669-714).
+
+``PackedCorpus``         - device-resident bf16 corpus [tiles][F][128][dim] built from the
+                           reference's per-field fp32 memmaps (or any [N,d] slabs)
+``MultiFieldRetriever``  - exhaustive fused scoring + mixture + top-k (``search``), the
+                           reference-faithful union/rescore pipeline (``union_rescore``), field
+                           masking, per-field top-k, QRes emission
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, TextIO, Tuple
+
+import numpy as np
+import torch
+
+from .. import _native as nv
+from ..data.trec import QRes
+from .weighting import LinearWeights
+
+KCHUNK = 64   # the tensor-core path consumes K in 64-element (128-byte) chunks
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class PackedCorpus:
+    """bf16 corpus in the tile layout the scoring kernels stream (include/mfar_b200.h).
+
+    ``dim`` is zero-padded to a multiple of 64 (dot products are unchanged); queries are padded
+    the same way by ``prepare_queries``."""
+
+    def __init__(self, n_docs: int, n_fields: int, dim: int, device="cuda", normalize: bool = False):
+        if n_docs <= 0 or n_fields <= 0 or dim <= 0:
+            raise ValueError("n_docs, n_fields, dim must be positive")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PackedCorpus lives in HBM: device must be CUDA (no CPU path)")
+        self.n_docs, self.n_fields, self.dim = int(n_docs), int(n_fields), int(dim)
+        self.dim_pad = _round_up(self.dim, KCHUNK)
+        self.normalize = bool(normalize)
+        n_el = nv.lib().mfar_corpus_packed_elems(self.n_docs, self.n_fields, self.dim_pad)
+        self.data = torch.zeros(n_el, dtype=torch.bfloat16, device=self.device)
+
+    # ------------------------------------------------------------------ loading
+    def load_rows(self, field: int, row_begin: int, rows: torch.Tensor) -> None:
+        """rows: [n, dim] fp32/bf16 tensor (host or device) -> docs [row_begin, row_begin+n) of `field`."""
+        if rows.dim() != 2 or rows.shape[1] != self.dim:
+            raise ValueError(f"expected [n,{self.dim}] rows, got {tuple(rows.shape)}")
+        r = rows.to(self.device, non_blocking=True)
+        if r.dtype not in (torch.float32, torch.bfloat16):
+            r = r.float()
+        if self.dim_pad != self.dim:
+            r = torch.nn.functional.pad(r, (0, self.dim_pad - self.dim))
+        r = r.contiguous()
+        code = nv.F32 if r.dtype == torch.float32 else nv.BF16
+        nv.check(nv.lib().mfar_corpus_pack_rows(nv.ptr(r), code, r.shape[0], int(row_begin), nv.ptr(self.data),
+                                                self.n_docs, self.n_fields, int(field), self.dim_pad,
+                                                int(self.normalize), nv.stream()), "corpus_pack_rows")
+
+    def load_field(self, field: int, vectors, chunk_rows: int = 131072) -> None:
+        """vectors: np.memmap / ndarray / tensor [N, dim] (the reference's ``MemoryMapDict.file``)."""
+        n = vectors.shape[0]
+        if n != self.n_docs:
+            raise ValueError(f"field has {n} rows, corpus has {self.n_docs}")
+        for lb in range(0, n, chunk_rows):
+            ub = min(n, lb + chunk_rows)
+            chunk = vectors[lb:ub]
+            if not torch.is_tensor(chunk):
+                chunk = torch.from_numpy(np.ascontiguousarray(chunk))
+            self.load_rows(field, lb, chunk)
+
+    @classmethod
+    def from_fields(cls, fields: Sequence, device="cuda", normalize: bool = False) -> "PackedCorpus":
+        """fields: F array-likes [N, dim], in scorer column order (``resolve_fields`` order)."""
+        n, d = fields[0].shape
+        pc = cls(n, len(fields), d, device, normalize)
+        for f, v in enumerate(fields):
+            pc.load_field(f, v)
+        return pc
+
+    @classmethod
+    def from_vectors_dict(cls, vectors_dict: Dict[str, "object"], dense_keys: Sequence[str], device="cuda",
+                          normalize: bool = False) -> "PackedCorpus":
+        """vectors_dict: field key -> MemoryMapDict, as returned by ``read_and_create_indices``."""
+        return cls.from_fields([vectors_dict[k].file for k in dense_keys], device, normalize)
+
+    def unpack_field(self, field: int, row_begin: int = 0, n_rows: Optional[int] = None) -> torch.Tensor:
+        n_rows = self.n_docs - row_begin if n_rows is None else n_rows
+        out = torch.empty((n_rows, self.dim_pad), dtype=torch.float32, device=self.device)
+        nv.check(nv.lib().mfar_corpus_unpack_rows(nv.ptr(self.data), self.n_docs, self.n_fields, int(field),
+                                                  self.dim_pad, int(row_begin), int(n_rows), nv.ptr(out), nv.stream()),
+                 "corpus_unpack_rows")
+        return out[:, : self.dim]
+
+    def prepare_queries(self, q_vecs) -> torch.Tensor:
+        """[Q, dim] (any float dtype, host or device) -> contiguous bf16 [Q, dim_pad] on the device."""
+        if not torch.is_tensor(q_vecs):
+            q_vecs = torch.from_numpy(np.ascontiguousarray(q_vecs))
+        if q_vecs.dim() != 2 or q_vecs.shape[1] != self.dim:
+            raise ValueError(f"expected [Q,{self.dim}] query vectors, got {tuple(q_vecs.shape)}")
+        q = q_vecs.to(self.device)
+        if self.normalize:
+            q = torch.nn.functional.normalize(q.float(), p=2, dim=1)
+        q = q.to(torch.bfloat16)
+        if self.dim_pad != self.dim:
+            q = torch.nn.functional.pad(q, (0, self.dim_pad - self.dim))
+        return q.contiguous()
+
+
+class MultiFieldRetriever:
+    """Scores every doc of a shard under all fields, mixes, keeps the top-k - one corpus pass.
+
+    Field order everywhere (W columns, mask rows, weights) is dense fields then sparse fields,
+    as ``resolve_fields`` produces (schema.py:130-134)."""
+
+    def __init__(self, corpus: Optional[PackedCorpus], mixture: LinearWeights, n_sparse: int = 0, top_k: int = 100,
+                 doc_id_base: int = 0, n_docs: Optional[int] = None, impl: str = "auto",
+                 numeric_ids_to_keys: Optional[Sequence[str]] = None, device=None):
+        self.corpus = corpus
+        self.n_dense = corpus.n_fields if corpus is not None else 0
+        self.n_sparse = int(n_sparse)
+        self.n_docs = corpus.n_docs if corpus is not None else int(n_docs)
+        self.device = corpus.device if corpus is not None else torch.device(device or "cuda")
+        self.mixture = mixture
+        if mixture.num_fields != self.n_dense + self.n_sparse:
+            raise ValueError(f"mixture has {mixture.num_fields} fields, retriever {self.n_dense}+{self.n_sparse}")
+        self.top_k = int(top_k)
+        self.doc_id_base = int(doc_id_base)
+        self.impl = impl
+        self.numeric_ids_to_keys = numeric_ids_to_keys
+        self.mask = torch.ones([self.num_fields, 1], device=self.device)      # contrastive.py:270
+        self.masked_fields_string = ""
+        self._ws: Optional[torch.Tensor] = None
+        self._host_scratch: Optional[torch.Tensor] = None
+        self.last_launches = 0
+
+    @property
+    def num_fields(self) -> int:
+        return self.n_dense + self.n_sparse
+
+    # ------------------------------------------------------------------ masking (contrastive.py:706-714)
+    def mask_field(self, field_idx_list: Sequence[int], field_names: Optional[Sequence[str]] = None) -> None:
+        mask = torch.ones([self.num_fields, 1], device=self.device)
+        mask[list(field_idx_list)] = 0
+        self.mask = mask
+        if field_names is not None:
+            self.masked_fields_string = ",".join(field_names[i] for i in field_idx_list)
+
+    # ------------------------------------------------------------------ internals
+    def _workspace(self, Q: int, k: int, n_sparse: int, n_docs: Optional[int] = None) -> torch.Tensor:
+        need = nv.lib().mfar_score_topk_workspace_bytes(Q, k, self.n_docs if n_docs is None else n_docs, n_sparse)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _check_sparse(self, sparse: Optional[torch.Tensor], Q: int) -> Tuple[Optional[torch.Tensor], int]:
+        if self.n_sparse == 0:
+            return None, nv.F16
+        if sparse is None:
+            raise ValueError(f"retriever has {self.n_sparse} sparse fields: pass their precomputed scores [Q,Fs,N]")
+        nv.require_device(sparse, "sparse")
+        if tuple(sparse.shape) != (Q, self.n_sparse, self.n_docs):
+            raise ValueError(f"sparse must be [{Q},{self.n_sparse},{self.n_docs}], got {tuple(sparse.shape)}")
+        if sparse.dtype not in (torch.float16, torch.float32):
+            sparse = sparse.float()
+        return sparse.contiguous(), (nv.F16 if sparse.dtype == torch.float16 else nv.F32)
+
+    def _score_topk(self, q_bf16: Optional[torch.Tensor], w: torch.Tensor, sparse, sparse_code: int, k: int,
+                    field_begin: int, n_dense: int, n_sparse: int, want_keys: bool = False, impl: Optional[str] = None,
+                    n_docs: Optional[int] = None, doc_id_base: Optional[int] = None):
+        Q = w.shape[0]
+        n_docs = self.n_docs if n_docs is None else n_docs
+        doc_id_base = self.doc_id_base if doc_id_base is None else doc_id_base
+        if k > n_docs:
+            raise RuntimeError(f"selected index k out of range (k={k}, docs={n_docs})")   # torch.topk's error
+        scores = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        ids = torch.empty((Q, k), dtype=torch.int64, device=self.device)
+        keys = torch.empty((Q, k), dtype=torch.int64, device=self.device) if want_keys else None
+        ws = self._workspace(Q, k, n_sparse, n_docs)
+        c = self.corpus
+        nv.check(nv.lib().mfar_score_topk(
+            nv.ptr(c.data) if c is not None else 0, n_docs, c.n_fields if c is not None else 0, field_begin,
+            n_dense, c.dim_pad if c is not None else 0, nv.ptr(q_bf16), Q, nv.ptr(w), nv.ptr(sparse), n_sparse,
+            sparse_code, n_docs, doc_id_base, k, nv.ptr(keys), nv.ptr(scores), nv.ptr(ids), nv.ptr(ws),
+            ws.numel(), nv.IMPL[impl or self.impl], nv.stream()), "score_topk")
+        self.last_launches = nv.lib().mfar_last_launch_count()
+        return scores, ids, keys
+
+    # ------------------------------------------------------------------ exhaustive fused search
+    @torch.no_grad()
+    def search(self, q_vecs, q_emb: Optional[torch.Tensor] = None, sparse: Optional[torch.Tensor] = None,
+               top_k: Optional[int] = None, return_keys: bool = False, impl: Optional[str] = None):
+        """Exhaustive multi-field top-k.
+
+        q_vecs [Q,dim]: query vectors for the dense dots (rounded to bf16);
+        q_emb  [Q,E]  : fp32 query embedding for the mixture softmax (defaults to q_vecs, as in the
+                        reference where both come from the same encoder, contrastive.py:688-694);
+        sparse [Q,Fs,N]: precomputed per-field BM25 scores of this shard's docs (f16/f32).
+        Returns (scores [Q,k] fp32, ids [Q,k] int64) sorted by (score desc, id asc); with
+        return_keys also the packed uint64 keys (as int64) used for cross-shard merging."""
+        k = top_k or self.top_k
+        if self.corpus is not None:
+            q_bf16 = self.corpus.prepare_queries(q_vecs)
+            Q = q_bf16.shape[0]
+        else:
+            q_bf16, Q = None, sparse.shape[0]
+        if self.mixture.query_cond:
+            qe = q_emb if q_emb is not None else (q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs))
+            qe = qe.to(self.device).float()
+        else:
+            qe = None
+        w = self.mixture.field_weights(qe, self.mask, batch=Q)
+        sp, code = self._check_sparse(sparse, Q)
+        scores, ids, keys = self._score_topk(q_bf16, w, sp, code, k, 0, self.n_dense, self.n_sparse,
+                                             want_keys=return_keys, impl=impl)
+        return (scores, ids, keys) if return_keys else (scores, ids)
+
+    # ------------------------------------------------------------------ host-buffer end-to-end call
+    def search_host(self, q_vecs_host: torch.Tensor, q_emb_host: Optional[torch.Tensor] = None,
+                    sparse_host: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
+                    out_scores: Optional[torch.Tensor] = None, out_ids: Optional[torch.Tensor] = None,
+                    impl: Optional[str] = None):
+        """One C-ABI call with HOST buffers (``mfar_search_host``): H2D of the batch, mixture weights,
+        fused scoring + top-k, D2H of the [Q,k] result, stream sync.  q_vecs_host: bf16 [Q,dim_pad] host tensor
+        (pinned for full PCIe speed); q_emb_host fp32 [Q,E]; sparse_host f16/f32 [Q,Fs,N]."""
+        k = top_k or self.top_k
+        c = self.corpus
+        Q = q_vecs_host.shape[0] if q_vecs_host is not None else sparse_host.shape[0]
+        if c is not None and (q_vecs_host.dtype != torch.bfloat16 or q_vecs_host.shape[1] != c.dim_pad
+                              or q_vecs_host.is_cuda):
+            raise ValueError("q_vecs_host must be a host bf16 [Q, dim_pad] tensor")
+        E = self.mixture.weight.shape[0] if self.mixture.query_cond else 0
+        if self.mixture.query_cond and (q_emb_host is None or q_emb_host.dtype != torch.float32):
+            raise ValueError("q_emb_host must be a host fp32 [Q,E] tensor")
+        code = nv.F16
+        if self.n_sparse:
+            code = nv.F16 if sparse_host.dtype == torch.float16 else nv.F32
+        need = nv.lib().mfar_search_host_scratch_bytes(Q, c.dim_pad if c else 0, E, self.n_dense, self.n_sparse,
+                                                       self.n_docs, code, k)
+        if self._host_scratch is None or self._host_scratch.numel() < need:
+            self._host_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if out_scores is None:
+            out_scores = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+        if out_ids is None:
+            out_ids = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+        W = self.mixture.weight.detach().contiguous().float()
+        m = self.mask.reshape(-1).contiguous().float()
+        nv.check(nv.lib().mfar_search_host(
+            nv.ptr(c.data) if c else 0, self.n_docs, c.n_fields if c else 0, 0, self.n_dense, c.dim_pad if c else 0,
+            nv.ptr(q_vecs_host), nv.ptr(q_emb_host), Q, E, nv.ptr(W), nv.ptr(m), int(self.mixture.query_cond),
+            nv.ptr(sparse_host), self.n_sparse, code, self.doc_id_base, k, nv.ptr(out_scores), nv.ptr(out_ids),
+            nv.ptr(self._host_scratch), self._host_scratch.numel(), nv.IMPL[impl or self.impl], nv.stream()),
+            "search_host")
+        self.last_launches = nv.lib().mfar_last_launch_count()
+        return out_scores, out_ids
+
+    # ------------------------------------------------------------------ per-field top-k (index.py:181-222)
+    @torch.no_grad()
+    def per_field_topk(self, q_vecs, sparse: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
+                       zero_init: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """What ``index.retrieve_batch(queries, top_k)`` returns for every field, in field order:
+        (scores [F,Q,k], rows [F,Q,k]).  Dense fields reproduce the reference's (0.0, row 0) running-top-k
+        initialisation (index.py:192-193) when zero_init is set."""
+        k = top_k or self.top_k
+        q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
+        Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
+        sp, code = self._check_sparse(sparse, Q)
+        ones = torch.ones((Q, 1), dtype=torch.float32, device=self.device)
+        all_s, all_i = [], []
+        for f in range(self.n_dense):
+            s, i, _ = self._score_topk(q_bf16, ones, None, nv.F16, k, f, 1, 0)
+            i = i - self.doc_id_base
+            if zero_init:
+                nv.check(nv.lib().mfar_topk_apply_zero_init(nv.ptr(s), nv.ptr(i), Q, k, nv.stream()), "zero_init")
+            all_s.append(s)
+            all_i.append(i)
+        for j in range(self.n_sparse):
+            sj = sp[:, j:j + 1, :].contiguous()
+            s, i, _ = self._score_topk(None, ones, sj, code, k, 0, 0, 1)
+            all_s.append(s)
+            all_i.append(i - self.doc_id_base)
+        return torch.stack(all_s), torch.stack(all_i)
+
+    # ------------------------------------------------------------------ candidate re-scoring (index.py:227-232)
+    @torch.no_grad()
+    def score_candidates(self, q_vecs, rows: torch.Tensor, sparse: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Per-field scores of the given local rows: [F, Q, C] (rows < 0 -> 0, index.py:112-117)."""
+        q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
+        Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
+        rows = rows.to(self.device, dtype=torch.int64).contiguous()
+        C = rows.numel()
+        out = torch.zeros((self.num_fields, Q, C), dtype=torch.float32, device=self.device)
+        if self.n_dense and C:
+            c = self.corpus
+            nv.check(nv.lib().mfar_score_candidates(nv.ptr(c.data), self.n_docs, c.n_fields, 0, self.n_dense,
+                                                    c.dim_pad, nv.ptr(q_bf16), Q, nv.ptr(rows), C, nv.ptr(out),
+                                                    nv.stream()), "score_candidates")
+        if self.n_sparse and C:
+            sp, _ = self._check_sparse(sparse, Q)
+            g = sp[:, :, rows.clamp(min=0)].float()                       # [Q,Fs,C] gather (index.py:116)
+            g = g * (rows >= 0).to(g.dtype)                               # unknown keys -> 0 (index.py:117)
+            out[self.n_dense:] = g.permute(1, 0, 2)
+        return out
+
+    # ------------------------------------------------------------------ faithful pipeline (contrastive.py:669-704)
+    @torch.no_grad()
+    def union_rescore(self, q_vecs, q_emb: Optional[torch.Tensor] = None, sparse: Optional[torch.Tensor] = None,
+                      top_k: Optional[int] = None) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+        """per-field top-k -> union -> rescore -> * mask -> mixture -> top-k, per query.
+        Returns per query (values [k], local rows [k])."""
+        k = top_k or self.top_k
+        _, rows = self.per_field_topk(q_vecs, sparse, k)                   # [F,Q,k]
+        Q = rows.shape[1]
+        qv = q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs)
+        qe = (q_emb if q_emb is not None else qv).to(self.device).float()
+        out_v, out_r = [], []
+        for i in range(Q):
+            union = torch.unique(rows[:, i, :].reshape(-1))               # sorted ascending
+            per_field = self.score_candidates(qv[i:i + 1], union, None if sparse is None else sparse[i:i + 1])
+            all_tens = per_field.squeeze(1) * self.mask                   # [F,U] * [F,1]   contrastive.py:686
+            scores = self.mixture(all_tens.t().contiguous(), qe[i:i + 1] if self.mixture.query_cond else None)
+            if scores.shape[1] < k:
+                raise RuntimeError("selected index k out of range")       # what torch.topk raises in the reference
+            # final top-k of the mixed union scores (contrastive.py:696) with the same streaming top-k kernel:
+            # the [1,U] score row is fed as a single pre-scored "field" of a U-doc shard
+            vals, idx, _ = self._score_topk(None, torch.ones((1, 1), dtype=torch.float32, device=self.device),
+                                            scores.reshape(1, 1, -1).contiguous(), nv.F32, k, 0, 0, 1,
+                                            n_docs=scores.shape[1], doc_id_base=0)
+            out_v.append(vals[0])
+            out_r.append(union[idx[0]])
+        return out_v, out_r
+
+    # ------------------------------------------------------------------ QRes emission (contrastive.py:696-704)
+    def trec_eval_step(self, query_ids: Sequence[str], q_vecs, qres_output: TextIO, q_emb=None, sparse=None,
+                       mode: str = "exhaustive") -> None:
+        if self.numeric_ids_to_keys is None:
+            raise RuntimeError("trec_eval_step needs numeric_ids_to_keys to name documents")
+        if mode == "exhaustive":
+            scores, ids = self.search(q_vecs, q_emb, sparse)
+            scores, ids = scores.cpu().tolist(), (ids - self.doc_id_base).cpu().tolist()
+        elif mode == "union_rescore":
+            v, r = self.union_rescore(q_vecs, q_emb, sparse)
+            scores, ids = [x.cpu().tolist() for x in v], [x.cpu().tolist() for x in r]
+        else:
+            raise ValueError(mode)
+        for qid, svals, rows in zip(query_ids, scores, ids):
+            for sim, row in zip(svals, rows):
+                print(QRes(query_id=qid, doc_id=self.numeric_ids_to_keys[row], sim=sim), file=qres_output)
