@@ -27,6 +27,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define MFAR_API __attribute__((visibility("default")))
+#else
+#define MFAR_API
+#endif
+
 #define MFAR_ABI_VERSION 1
 #define MFAR_TILE_DOCS 128   /* docs per corpus tile (UMMA M)                       */
 #define MFAR_MAX_K 128       /* top-k depth limit (reference hard-codes k = 100)    */
@@ -51,10 +57,10 @@ typedef enum mfar_impl {
   MFAR_IMPL_TCGEN05 = 2 /* TMA + tcgen05.mma + TMEM path                              */
 } mfar_impl;
 
-int mfar_abi_version(void);
-const char* mfar_status_string(int status);
+MFAR_API int mfar_abi_version(void);
+MFAR_API const char* mfar_status_string(int status);
 /* 0 when `device` (or the current device if < 0) can run this library (sm_100). */
-int mfar_device_check(int device);
+MFAR_API int mfar_device_check(int device);
 
 /* ------------------------------------------------------------------------------------------
  * Corpus store.  Replaces: the per-field headerless fp32 memmaps {temp_dir}/{field.name}.npy
@@ -65,19 +71,19 @@ int mfar_device_check(int device);
  *   n_tiles = ceil(n_docs / 128); rows of the last tile beyond n_docs are zero.
  * One (tile, field) block is 128*dim*2 contiguous bytes = one TMA box column.
  * ------------------------------------------------------------------------------------------ */
-int64_t mfar_corpus_packed_elems(int64_t n_docs, int n_fields, int dim);
+MFAR_API int64_t mfar_corpus_packed_elems(int64_t n_docs, int n_fields, int dim);
 
 /* Convert rows [row_begin, row_begin + n_rows) of ONE field from a row-major [n_rows, dim]
  * slab (fp32 or bf16) into the packed corpus; optional per-row L2 normalisation (the
  * reference's Normalize() module, mfar/modeling/util.py:50-51) before rounding to bf16.
  * Call once per (field, slab); slabs may arrive in any order.  Zero the packed buffer first
  * if n_docs is not a multiple of 128. */
-int mfar_corpus_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin,
+MFAR_API int mfar_corpus_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin,
                           void* packed, int64_t n_docs, int n_fields, int field, int dim,
                           int normalize, void* stream);
 
 /* Inverse view for tests / candidate export: copy rows of one field out as fp32 [n_rows, dim]. */
-int mfar_corpus_unpack_rows(const void* packed, int64_t n_docs, int n_fields, int field, int dim,
+MFAR_API int mfar_corpus_unpack_rows(const void* packed, int64_t n_docs, int n_fields, int field, int dim,
                             int64_t row_begin, int64_t n_rows, float* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -89,11 +95,11 @@ int mfar_corpus_unpack_rows(const void* packed, int64_t n_docs, int n_fields, in
  * mask may be NULL (all ones).  The mask multiplies AFTER the softmax: masked fields keep
  * their softmax mass, weights are not renormalised - exactly contrastive.py:686 followed by
  * weighting.py:28-29.  fp32 throughout. */
-int mfar_mixture_weights(const float* q_emb, const float* W, const float* mask, int Q, int E, int F,
+MFAR_API int mfar_mixture_weights(const float* q_emb, const float* W, const float* mask, int Q, int E, int F,
                          int query_cond, float* out_w, void* stream);
 
 /* out[b,s] = sum_f w[b or 0, f] * x[b,s,f]   (weighting.py:29).  w_rows is Q or 1. */
-int mfar_mixture_apply(const float* x, const float* w, int B, int S, int F, int w_rows, float* out,
+MFAR_API int mfar_mixture_apply(const float* x, const float* w, int B, int S, int F, int w_rows, float* out,
                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -118,9 +124,9 @@ int mfar_mixture_apply(const float* x, const float* w, int B, int S, int F, int 
  * out_keys      optional uint64 [Q,k]: order-preserving (score,id) keys for mfar_topk_merge
  * out_scores    fp32 [Q,k];  out_ids  int64 [Q,k];  slots beyond n_docs: (-inf, -1)
  * ------------------------------------------------------------------------------------------ */
-size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse);
+MFAR_API size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse);
 
-int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
+MFAR_API int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
                     int dim, const void* q_vecs, int Q, const float* w, const void* sparse, int n_sparse,
                     int sparse_dtype, int64_t sparse_ld, int64_t doc_id_base, int k, uint64_t* out_keys,
                     float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, int impl,
@@ -130,13 +136,13 @@ int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int f
  * per-CTA partial lists inside mfar_score_topk and (b) the per-shard lists after the NCCL
  * all-gather (replaces the {rank}.qres file merge of mfar/modeling/contrastive.py:616-631).
  * keys: uint64 [L, Q, k_in]; key 0 = empty slot. */
-int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_t* out_keys,
+MFAR_API int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_t* out_keys,
                     float* out_scores, int64_t* out_ids, void* stream);
 
 /* Reference quirk, mfar/data/index.py:192-193: the running top-k starts as k entries of
  * (score 0.0, row 0).  Applies that to a finished [Q,k] result in place: entries scoring
  * below 0.0 are replaced by (0.0, 0) and the list re-sorted. */
-int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* stream);
+MFAR_API int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Candidate re-scoring.  Replaces DenseFlatIndex.score_batch (mfar/data/index.py:227-232) and
@@ -144,7 +150,7 @@ int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* s
  * trec_eval_step (contrastive.py:681-683).
  *   out[f, q, c] = <q_vec[q], corpus[rows[c], field_begin+f]>      rows[c] < 0 -> 0
  * ------------------------------------------------------------------------------------------ */
-int mfar_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin,
+MFAR_API int mfar_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin,
                           int n_fields, int dim, const void* q_vecs, int Q, const int64_t* rows, int C,
                           float* out, void* stream);
 
@@ -156,17 +162,25 @@ int mfar_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields,
  * pointers (model state); sparse_host may be NULL.  scratch: device buffer of at least
  * mfar_search_host_scratch_bytes(...) bytes.
  * ------------------------------------------------------------------------------------------ */
-size_t mfar_search_host_scratch_bytes(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
+MFAR_API size_t mfar_search_host_scratch_bytes(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
                                       int sparse_dtype, int k);
 
-int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
+MFAR_API int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
                      int dim, const void* q_vecs_host, const float* q_emb_host, int Q, int E, const float* W,
                      const float* mask, int query_cond, const void* sparse_host, int n_sparse,
                      int sparse_dtype, int64_t doc_id_base, int k, float* out_scores_host,
                      int64_t* out_ids_host, void* scratch, size_t scratch_bytes, int impl, void* stream);
 
 /* Number of kernels the last mfar_score_topk call on this thread launched (bench bookkeeping). */
-int mfar_last_launch_count(void);
+MFAR_API int mfar_last_launch_count(void);
+
+/* Per-launch device timing of the scoring kernel (the dominant kernel of a step), for the roofline
+ * bench.py reports.  mfar_profile_enable(1) arms a ring of 256 CUDA event pairs recorded on the launch
+ * stream around the scoring kernel of each subsequent mfar_score_topk call; mfar_profile_collect()
+ * synchronises those events, writes their durations (ms) to a HOST array, returns how many, and
+ * resets the ring. */
+MFAR_API int mfar_profile_enable(int on);
+MFAR_API int mfar_profile_collect(float* out_ms_host, int max_n);
 
 #ifdef __cplusplus
 }

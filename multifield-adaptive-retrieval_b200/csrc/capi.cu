@@ -8,6 +8,14 @@ using namespace mfar;
 
 static thread_local int t_last_launches = 0;
 
+// Optional per-launch timing of the scoring kernel (bench.py's roofline): a ring of CUDA event pairs recorded
+// on the launch stream around the scoring kernel only.  Off by default; costs two event records per call.
+constexpr int kProfRing = 256;
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[kProfRing][2];
+static bool g_prof_init = false;
+static int g_prof_n = 0;
+
 static int check_arch() {
   static int cached = -1;   // one process per GPU
   if (cached >= 0) return cached;
@@ -167,11 +175,14 @@ int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int f
     a.base_ld = base_ld;
   }
   int rc;
+  const bool prof = g_prof_on && g_prof_n < kProfRing;
+  if (prof) MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][0], st));
   if (g.impl == MFAR_IMPL_TCGEN05)
     rc = launch_score_tc(a, workspace, g.workers, g.q_tiles, g.q_pad, st);
   else
     rc = launch_score_simt(a, workspace, g.workers, g.q_pad, st);
   if (rc) return rc;
+  if (prof) { MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][1], st)); ++g_prof_n; }
   ++t_last_launches;
   TopkWorkspace ws = carve_workspace(workspace, g.workers, g.q_pad_total);
   rc = launch_merge(ws.cand_keys, ws.cand_cnt, ws.cand_thr, g.workers, g.q_pad_total, kCandCap, Q, k, out_keys,
@@ -274,5 +285,26 @@ int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int 
 }
 
 int mfar_last_launch_count(void) { return t_last_launches; }
+
+int mfar_profile_enable(int on) {
+  if (on && !g_prof_init) {
+    for (int i = 0; i < kProfRing; ++i)
+      for (int j = 0; j < 2; ++j) MFAR_CUDA_OK(cudaEventCreate(&g_prof_ev[i][j]));
+    g_prof_init = true;
+  }
+  g_prof_on = on != 0;
+  g_prof_n = 0;
+  return MFAR_OK;
+}
+
+int mfar_profile_collect(float* out_ms_host, int max_n) {
+  int n = g_prof_n < max_n ? g_prof_n : max_n;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_prof_ev[i][1]) != cudaSuccess) return -1;
+    if (cudaEventElapsedTime(&out_ms_host[i], g_prof_ev[i][0], g_prof_ev[i][1]) != cudaSuccess) return -1;
+  }
+  g_prof_n = 0;
+  return n;
+}
 
 }  // extern "C"

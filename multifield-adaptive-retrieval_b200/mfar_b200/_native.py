@@ -41,6 +41,8 @@ PROTOTYPES = {
     "mfar_search_host": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i64, _i,
                               _vp, _vp, _vp, _sz, _i, _vp]),
     "mfar_last_launch_count": (_i, []),
+    "mfar_profile_enable": (_i, [_i]),
+    "mfar_profile_collect": (_i, [_vp, _i]),
 }
 
 

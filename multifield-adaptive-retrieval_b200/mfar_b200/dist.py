@@ -44,9 +44,10 @@ def decode_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
 def all_gather_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
     """keys: int64 view of the packed uint64 keys [Q,k] -> [R,Q,k] (same on every rank)."""
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
-    dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
-    return out
+    keys = keys.contiguous()
+    out = torch.empty((world * keys.shape[0],) + tuple(keys.shape[1:]), dtype=keys.dtype, device=keys.device)
+    dist.all_gather_into_tensor(out, keys, group=group)          # concatenated along dim 0 (gloo and nccl)
+    return out.view((world,) + tuple(keys.shape))
 
 
 def merge_keys(all_keys: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -1,0 +1,331 @@
+"""CUDA path vs oracle / reference-generated golden vectors.  Every call goes through the C ABI
+(ctypes -> libmfar_b200.so).  Bar: ids identical except near-ties, scores within 1e-2 relative of
+the fp32 reference on identical bf16-rounded inputs (asserted at 2e-5, tests/parity.py)."""
+import glob
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import mfar_oracle as O
+from parity import assert_topk_parity
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+IMPLS = ["simt", "tcgen05"]
+DEV = "cuda"
+
+
+def _mods():
+    from mfar_b200.modeling.retrieval import MultiFieldRetriever, PackedCorpus
+    from mfar_b200.modeling.weighting import LinearWeights
+    return MultiFieldRetriever, PackedCorpus, LinearWeights
+
+
+def load(path):
+    z = np.load(path, allow_pickle=False)
+    return z, json.loads(str(z["meta"]))
+
+
+def build(fields, W, query_cond, n_sparse=0, k=100, normalize=False, doc_id_base=0, impl="auto"):
+    MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    pc = PackedCorpus.from_fields(fields, DEV, normalize) if len(fields) else None
+    F = len(fields) + n_sparse
+    layer = LinearWeights(W.shape[0], W.shape[1], query_cond=True) if query_cond else LinearWeights(F, 1)
+    with torch.no_grad():
+        layer.weight.copy_(torch.as_tensor(W))
+    layer = layer.to(DEV)
+    n_docs = fields[0].shape[0] if len(fields) else None
+    return MultiFieldRetriever(pc, layer, n_sparse=n_sparse, top_k=k, doc_id_base=doc_id_base, impl=impl,
+                               n_docs=n_docs, device=DEV)
+
+
+def synth(seed, N, d, Fd, Fs, Q, query_cond=True):
+    g = torch.Generator().manual_seed(seed)
+    mu = torch.randn(d, generator=g)
+    fields = [O.round_bf16(torch.randn(N, d, generator=g) + 0.5 * mu) for _ in range(Fd)]
+    q = O.round_bf16(torch.randn(Q, d, generator=g) + 0.5 * mu)
+    sp = None
+    if Fs:
+        u = torch.rand(Q, Fs, N, generator=g)
+        gam = -2.0 * (torch.log(torch.rand(Q, Fs, N, generator=g)) + torch.log(torch.rand(Q, Fs, N, generator=g)))
+        sp = torch.where(u < 0.95, torch.zeros(()), gam).half()
+    F = Fd + Fs
+    W = 0.05 * torch.randn(d, F, generator=g) if query_cond else torch.randn(F, 1, generator=g)
+    return fields, q, sp, W
+
+
+# ----------------------------------------------------------------------------------------------
+def test_device_is_sm100_and_library_loaded():
+    from mfar_b200 import _native as nv
+    assert nv.lib().mfar_device_check(-1) == 0
+    assert torch.cuda.get_device_capability()[0] == 10
+
+
+def test_pack_unpack_roundtrip_bit_exact():
+    _, PackedCorpus, _ = _mods()
+    g = torch.Generator().manual_seed(1)
+    for N, d, F in [(300, 64, 3), (129, 768, 2), (128, 32, 1)]:
+        fields = [torch.randn(N, d, generator=g) for _ in range(F)]
+        pc = PackedCorpus.from_fields(fields, DEV)
+        for f in range(F):
+            got = pc.unpack_field(f).cpu()
+            assert torch.equal(got, fields[f].to(torch.bfloat16).float())
+        assert pc.data.numel() == ((N + 127) // 128) * F * 128 * pc.dim_pad
+    # normalize=True == torch.nn.functional.normalize then bf16 rounding
+    pcn = PackedCorpus.from_fields([fields[0]], DEV, normalize=True)
+    ref = torch.nn.functional.normalize(fields[0], dim=1)
+    torch.testing.assert_close(pcn.unpack_field(0).cpu(), ref.to(torch.bfloat16).float(), rtol=0, atol=1e-2)
+
+
+@pytest.mark.parametrize("query_cond", [True, False])
+def test_mixture_weights_and_forward_match_oracle(query_cond):
+    _, _, LinearWeights = _mods()
+    g = torch.Generator().manual_seed(2)
+    B, S, E, F = 5, 37, 768, 22
+    W = 0.05 * torch.randn(E, F, generator=g) if query_cond else torch.randn(F, 1, generator=g)
+    q = torch.randn(B, E, generator=g)
+    x = torch.randn(B, S, F, generator=g)
+    layer = LinearWeights(E, F, query_cond=True) if query_cond else LinearWeights(F, 1)
+    with torch.no_grad():
+        layer.weight.copy_(W)
+    layer = layer.to(DEV)
+    mask = torch.ones(F, 1)
+    mask[3] = 0
+    w = layer.field_weights(q.to(DEV) if query_cond else None, mask.to(DEV), batch=B).cpu()
+    ref_w = O.mixture_weights(q, W, query_cond).expand(B, F) * mask.reshape(1, F)
+    torch.testing.assert_close(w, ref_w, rtol=2e-5, atol=1e-7)
+    out = layer(x.to(DEV), q.to(DEV) if query_cond else None).cpu()
+    torch.testing.assert_close(out, O.linear_weights_forward(x, q, W, query_cond), rtol=2e-5, atol=1e-5)
+    out2 = layer(x[0].to(DEV), q[:1].to(DEV) if query_cond else None).cpu()          # [S,F] form of trec_eval_step
+    assert out2.shape == (1, S)
+    torch.testing.assert_close(out2, O.linear_weights_forward(x[0], q[:1], W, query_cond), rtol=2e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_exhaustive_search_vs_reference_golden(path, impl):
+    """Top-k of the CUDA path against the all-doc mixture scores the REFERENCE's own LinearWeights /
+    DenseFlatIndex / BM25sSparseIndex.score_batch produced (tests/golden, ref_mix_all)."""
+    z, m = load(path)
+    fields = [torch.from_numpy(z["fields"][f]) for f in range(m["Fd"])]
+    sp = torch.from_numpy(z["sparse"]).to(DEV) if m["Fs"] else None
+    k = m["k"]
+    r = build(fields, z["W"], m["query_cond"], m["Fs"], k, impl=impl)
+    r.mask = torch.from_numpy(z["mask"]).to(DEV)
+    q = torch.from_numpy(z["q"])
+    scores, ids = r.search(q.to(DEV), q.to(DEV), sp)
+    assert_topk_parity(scores.cpu().numpy(), ids.cpu().numpy(), z["ref_mix_all"], k)
+    # fp16 and fp32 sparse inputs agree (golden sparse values are fp16-representable)
+    if sp is not None:
+        s2, i2 = r.search(q.to(DEV), q.to(DEV), sp.half())
+        assert torch.equal(i2, ids) and torch.equal(s2, scores)
+
+
+SHAPES = [
+    # seed, N, d, Fd, Fs, Q, query_cond, k
+    (21, 2000, 768, 22, 0, 64, True, 100),      # config 1 shape (PRIME truncated, all_dense, dev batch 64)
+    (22, 1500, 768, 5, 0, 1, True, 100),        # MAG-shaped, batch 1
+    (23, 1111, 768, 8, 8, 3, True, 100),        # Amazon-shaped hybrid, ragged N
+    (24, 900, 768, 1, 0, 5, False, 100),        # single_dense, static weights
+    (25, 700, 768, 0, 4, 6, False, 50),         # sparse only
+    (26, 3000, 768, 3, 2, 70, True, 100),       # Q > 64: two query tiles on the tcgen05 path
+    (27, 129, 64, 2, 1, 17, True, 100),         # 2 tiles, the second with a single doc
+    (28, 128, 128, 4, 0, 33, True, 128),        # k = 128 = N (everything returned)
+    (29, 5000, 256, 2, 0, 130, True, 10),       # three query tiles
+]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"s{s[0]}" for s in SHAPES])
+def test_exhaustive_search_vs_oracle(shape, impl):
+    seed, N, d, Fd, Fs, Q, qc, k = shape
+    if impl == "tcgen05" and Fd == 0:
+        pytest.skip("sparse-only batches have no dense contraction: SIMT path by design")
+    fields, q, sp, W = synth(seed, N, d, Fd, Fs, Q, qc)
+    r = build(fields, W, qc, Fs, k, impl=impl) if Fd else build([], W, qc, Fs, k, impl=impl)
+    if not Fd:
+        r.n_docs = N
+    mask = torch.ones(Fd + Fs, 1)
+    if Fd + Fs > 2:
+        mask[1] = 0
+        r.mask_field([1])
+    scores, ids = r.search(q.to(DEV) if Fd else None, q.to(DEV), None if sp is None else sp.to(DEV))
+    w = O.mixture_weights(q if qc else None, W, qc)
+    ref = O.exhaustive_scores(q, fields, None if sp is None else sp.float(), w, mask) if Fd else \
+        O.exhaustive_scores(q, [], sp.float(), w, mask)
+    assert_topk_parity(scores.cpu().numpy(), ids.cpu().numpy(), ref.numpy(), k)
+
+
+def test_simt_and_tcgen05_agree_at_scale():
+    """Size-independent cross-check at a size the CPU oracle would take minutes for: both CUDA paths over
+    200k docs x 4 fields; ids equal except near-ties, scores within 2e-5; sortedness; uniqueness."""
+    MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    from mfar_b200 import synth as S
+    N, F, d, Q, k = 200_000, 4, 768, 4, 100
+    pc = PackedCorpus(N, F, d, DEV)
+    S.fill_packed_corpus(pc, seed=7)
+    mu = S.corpus_mean(d, 7, DEV)
+    q = S.make_queries(Q, d, mu, 8, DEV)
+    layer = LinearWeights(d, F, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(S.make_mixture(d, F, 9))
+    r = MultiFieldRetriever(pc, layer.to(DEV), top_k=k)
+    s1, i1 = r.search(q, q.float(), impl="simt")
+    s2, i2 = r.search(q, q.float(), impl="tcgen05")
+    for s, i in ((s1, i1), (s2, i2)):
+        assert (s[:, :-1] >= s[:, 1:]).all()
+        assert all(len(set(row.tolist())) == k for row in i.cpu())
+        assert i.min() >= 0 and i.max() < N
+    torch.testing.assert_close(s1, s2, rtol=2e-5, atol=1e-4)
+    agree = (i1 == i2).float().mean().item()
+    assert agree > 0.98, agree
+    # spot-check the winners against the oracle on the rows that were returned
+    rows = i2[0].cpu()
+    per_field = torch.stack([pc.unpack_field(f)[rows.to(DEV)].cpu() for f in range(F)])        # [F,k,d]
+    w = O.mixture_weights(q.float().cpu(), layer.weight.cpu(), True)[0]
+    ref = sum(w[f] * (per_field[f] @ q[0].float().cpu()) for f in range(F))
+    torch.testing.assert_close(s2[0].cpu(), ref, rtol=2e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_per_field_topk_vs_reference_retrieve_batch(path):
+    """DenseFlatIndex.retrieve_batch incl. the (0.0, row 0) running-top-k init (index.py:192-193)."""
+    z, m = load(path)
+    if m["Fd"] == 0:
+        pytest.skip("no dense field")
+    fields = [torch.from_numpy(z["fields"][f]) for f in range(m["Fd"])]
+    r = build(fields, np.ones((m["Fd"], 1), np.float32), False, 0, m["k"])
+    s, rows = r.per_field_topk(torch.from_numpy(z["q"]).to(DEV), None, m["k"])
+    s, rows = s.cpu().numpy(), rows.cpu().numpy()
+    ref_s, ref_r = z["ref_retrieve_scores"], z["ref_retrieve_rows"]
+    np.testing.assert_allclose(s, ref_s, rtol=2e-5, atol=2e-5 * np.abs(ref_s).max())
+    mism = rows != ref_r
+    for f, qi, j in np.argwhere(mism):                       # only (near-)ties may differ in order
+        near = np.abs(ref_s[f, qi] - ref_s[f, qi, j]) <= 1e-5 * max(1.0, np.abs(ref_s[f, qi]).max())
+        assert near.sum() > 1, (f, qi, j)
+
+
+def test_dense_flat_index_api_matches_reference_types():
+    from mfar_b200.data.index import DenseFlatIndex
+    z, m = load(os.path.join(GOLDEN, "d768_dense_static.npz"))
+    keys = [f"d{i}" for i in range(m["N"])]
+    idx = DenseFlatIndex(None, z["fields"][0], keys, {k: i for i, k in enumerate(keys)}, device=DEV)
+    hits = idx.retrieve_batch(z["q"], top_k=m["k"])
+    assert len(hits) == m["Q"] and len(hits[0]) == m["k"]
+    assert isinstance(hits[0][0][0], str) and isinstance(hits[0][0][1], float)
+    assert [h[0] for h in hits[0]] == [f"d{r}" for r in z["ref_retrieve_rows"][0, 0]]
+    cand = [keys[r] for r in z["cand_rows"]]
+    sb = idx.score_batch(z["q"], cand).cpu().numpy()
+    np.testing.assert_allclose(sb, z["ref_score_batch"][0], rtol=2e-5, atol=1e-4)
+    with pytest.raises(KeyError):
+        idx.score_batch(z["q"], ["nope"])
+    single = idx.retrieve(z["q"][:1], 5)
+    assert len(single) == 5
+    idx.vectors = z["fields"][1]                              # rebinding re-packs (contrastive.py:493-494)
+    assert [h[0] for h in idx.retrieve_batch(z["q"], m["k"])[1]] == [f"d{r}" for r in z["ref_retrieve_rows"][1, 1]]
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_score_candidates_vs_reference_score_batch(path):
+    z, m = load(path)
+    fields = [torch.from_numpy(z["fields"][f]) for f in range(m["Fd"])]
+    sp = torch.from_numpy(z["sparse"]).to(DEV) if m["Fs"] else None
+    F = m["Fd"] + m["Fs"]
+    r = build(fields, np.ones((F, 1), np.float32), False, m["Fs"], m["k"])
+    rows = torch.from_numpy(np.concatenate([z["cand_rows"], [-1]]))
+    out = r.score_candidates(torch.from_numpy(z["q"]).to(DEV), rows, sp).cpu().numpy()
+    np.testing.assert_allclose(out[: m["Fd"], :, :-1], z["ref_score_batch"], rtol=2e-5, atol=1e-4)
+    assert (out[:, :, -1] == 0).all()
+    if m["Fs"]:
+        np.testing.assert_array_equal(out[m["Fd"]:], z["ref_sparse_score_batch"])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
+def test_union_rescore_vs_reference_pipeline(path):
+    z, m = load(path)
+    fields = [torch.from_numpy(z["fields"][f]) for f in range(m["Fd"])]
+    sp = torch.from_numpy(z["sparse"]).to(DEV) if m["Fs"] else None
+    r = build(fields, z["W"], m["query_cond"], m["Fs"], m["k"])
+    r.mask = torch.from_numpy(z["mask"]).to(DEV)
+    q = torch.from_numpy(z["q"]).to(DEV)
+    if bool(z["ref_union_raises"]):
+        with pytest.raises(RuntimeError):
+            r.union_rescore(q, q, sp)
+        return
+    vals, rows = r.union_rescore(q, q, sp)
+    for i in range(m["Q"]):
+        ref_v, ref_r = z["ref_union_vals"][i], z["ref_union_rows"][i]
+        np.testing.assert_allclose(vals[i].cpu().numpy(), ref_v, rtol=2e-5, atol=1e-5)
+        got_r = rows[i].cpu().numpy()
+        for j in np.nonzero(got_r != ref_r)[0]:
+            assert (np.abs(ref_v - ref_v[j]) <= 1e-5 * max(1.0, np.abs(ref_v).max())).sum() > 1
+
+
+def test_search_host_equals_device_search_and_counts_launches():
+    fields, q, sp, W = synth(31, 1000, 768, 3, 2, 9, True)
+    r = build(fields, W, True, 2, 100)
+    s_dev, i_dev = r.search(q.to(DEV), q.to(DEV), sp.to(DEV))
+    assert r.last_launches == 3                         # sparse pre-mix + scoring + merge
+    qh = q.to(torch.bfloat16).pin_memory()
+    s_h, i_h = r.search_host(qh, q.float().pin_memory(), sp.pin_memory())
+    assert not s_h.is_cuda
+    assert torch.equal(s_h, s_dev.cpu()) and torch.equal(i_h, i_dev.cpu())
+    assert r.last_launches == 4                         # + mixture weights
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_virtual_shards_merge_equals_single_shard(impl):
+    """Shard-merge associativity: 1 vs 2/4/8 doc-range shards (run sequentially on one GPU, global ids,
+    keys merged by mfar_topk_merge) give bit-identical results."""
+    from mfar_b200.dist import merge_keys, shard_range
+    fields, q, sp, W = synth(41, 4000, 768, 3, 1, 5, True)
+    k = 100
+    full = build(fields, W, True, 1, k, impl=impl)
+    s0, i0, k0 = full.search(q.to(DEV), q.to(DEV), sp.to(DEV), return_keys=True)
+    for R in (2, 4, 8):
+        keys = []
+        for rank in range(R):
+            lo, hi = shard_range(4000, rank, R)
+            sh = build([f[lo:hi] for f in fields], W, True, 1, k, doc_id_base=lo, impl=impl)
+            _, _, kk = sh.search(q.to(DEV), q.to(DEV), sp[:, :, lo:hi].contiguous().to(DEV), return_keys=True)
+            keys.append(kk)
+        s, i = merge_keys(torch.stack(keys), k)
+        assert torch.equal(i, i0) and torch.equal(s, s0), R
+
+
+def test_topk_edge_cases():
+    fields, q, _, W = synth(51, 300, 64, 2, 0, 2, False)
+    r = build(fields, W, False, 0, 100)
+    with pytest.raises(RuntimeError):                   # reference: torch.topk raises when k > N
+        r.search(q.to(DEV), None, None, top_k=301)
+    # all-equal scores: deterministic tie-break = lowest doc ids first
+    zeros = [torch.zeros(300, 64)]
+    rz = build(zeros, np.ones((1, 1), np.float32), False, 0, 10)
+    s, i = rz.search(q.to(DEV))
+    assert (s == 0).all() and i.cpu().tolist() == [list(range(10))] * 2
+    # masks: masking every field but one == searching that field alone (weights not renormalised)
+    r.mask_field([0])
+    s1, i1 = r.search(q.to(DEV), top_k=20)
+    w = O.mixture_weights(None, W, False)
+    ref = O.exhaustive_scores(q, fields, None, w, torch.tensor([[0.0], [1.0]]))
+    assert_topk_parity(s1.cpu().numpy(), i1.cpu().numpy(), ref.numpy(), 20)
+
+
+def test_trec_eval_step_writes_qres_lines():
+    fields, q, _, W = synth(61, 400, 64, 2, 0, 3, True)
+    r = build(fields, W, True, 0, 100)
+    r.numeric_ids_to_keys = [f"doc{i}" for i in range(400)]
+    buf = io.StringIO()
+    r.trec_eval_step(["qa", "qb", "qc"], q.to(DEV), buf, q_emb=q.to(DEV))
+    lines = buf.getvalue().strip().split("\n")
+    assert len(lines) == 300
+    qid, it, doc, rank, sim, run = lines[0].split("\t")
+    assert qid == "qa" and it == "0" and doc.startswith("doc") and run == "0"
+    sims = [float(l.split("\t")[4]) for l in lines[:100]]
+    assert sims == sorted(sims, reverse=True)

@@ -1,0 +1,156 @@
+"""Host-side logic and the C-ABI surface - no GPU needed."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    from mfar_b200 import _native as nv
+    lib = nv.lib()                                   # raises if the .so is missing: no fallback
+    header = open(os.path.join(ROOT, "include", "mfar_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(mfar_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mfar_b200.h but not exported"
+    assert declared == set(nv.PROTOTYPES), "ctypes prototype table out of sync with the header"
+    assert lib.mfar_abi_version() == 1
+    assert lib.mfar_status_string(0) == b"ok"
+    assert b"sm_100" in lib.mfar_status_string(3)
+
+
+def test_geometry_helpers_without_gpu():
+    from mfar_b200 import _native as nv
+    lib = nv.lib()
+    assert lib.mfar_corpus_packed_elems(129375, 22, 768) == 1011 * 22 * 128 * 768
+    assert lib.mfar_corpus_packed_elems(128, 1, 64) == 128 * 64
+    assert lib.mfar_corpus_packed_elems(-1, 1, 64) == -1
+    small = lib.mfar_score_topk_workspace_bytes(1, 100, 10_000_000, 0)
+    big = lib.mfar_score_topk_workspace_bytes(512, 100, 10_000_000, 0)
+    assert 0 < small < big < (1 << 30)
+    assert lib.mfar_score_topk_workspace_bytes(64, 100, 129375, 22) > 64 * 129375 * 4
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_loudly_without_gpu():
+    from mfar_b200 import _native as nv
+    assert nv.lib().mfar_device_check(-1) != 0
+    out = (ctypes.c_float * 4)()
+    W = (ctypes.c_float * 4)()
+    rc = nv.lib().mfar_mixture_weights(None, ctypes.addressof(W), None, 1, 0, 4, 0, ctypes.addressof(out), None)
+    assert rc != 0
+    with pytest.raises(RuntimeError):
+        nv.check(rc, "mixture_weights")
+
+
+def test_wrappers_refuse_cpu_tensors():
+    from mfar_b200.data.index import DenseFlatIndex
+    from mfar_b200.modeling.retrieval import PackedCorpus
+    from mfar_b200.modeling.weighting import LinearWeights
+    with pytest.raises(RuntimeError):
+        PackedCorpus(10, 1, 64, device="cpu")
+    with pytest.raises(RuntimeError):
+        DenseFlatIndex(None, np.zeros((4, 8), np.float32), ["a"] * 4, {}, device="cpu")
+    layer = LinearWeights(8, 3, query_cond=True)
+    with pytest.raises(RuntimeError):
+        layer(torch.zeros(2, 5, 3), torch.zeros(2, 8))
+
+
+def test_resolve_fields_matches_reference_golden():
+    from mfar_b200 import resolve_fields
+    cases = json.load(open(os.path.join(GOLDEN, "resolve_fields.json")))
+    assert len(cases) >= 20
+    for key, expect in cases.items():
+        dataset, names = key.split("|")
+        if expect == "ValueError":
+            with pytest.raises(ValueError):
+                resolve_fields(names, dataset)
+            continue
+        got = resolve_fields(names, dataset)
+        assert [[k, f.name, f.field_type.name, f.max_seq_length] for k, f in got.items()] == expect
+    with pytest.raises(NotImplementedError):
+        resolve_fields("all_dense", "nope")
+    f = resolve_fields("all_dense,all_sparse", "prime")
+    assert len(f) == 44 and list(f)[:22] == sorted(list(f)[:22]) and list(f)[22:] == sorted(list(f)[22:])
+    assert len(resolve_fields("all_dense", "mag")) == 5 and len(resolve_fields("all_dense", "amazon")) == 8
+    assert resolve_fields("expression.absent_dense", "prime")["expression absent_dense"].name == "expression absent"
+
+
+def test_memory_map_dict_is_headerless_fp32(tmp_path):
+    from mfar_b200 import MemoryMapDict
+    path = str(tmp_path / "title.npy")
+    open(path, "w").close()
+    keys = [f"d{i}" for i in range(7)]
+    m = MemoryMapDict(path, keys, (7, 16))
+    for i, k in enumerate(keys):
+        m[k] = np.full(16, i, np.float32)
+    m.close()
+    m.reopen()
+    assert os.path.getsize(path) == 7 * 16 * 4                      # no .npy header (modeling/util.py:85-94)
+    raw = np.fromfile(path, dtype=np.float32).reshape(7, 16)
+    assert (raw[:, 0] == np.arange(7)).all() and (m["d3"] == 3).all()
+    assert len(m) == 7 and "d2" in m and "zz" not in m and list(m) == keys
+    with pytest.raises(NotImplementedError):
+        del m["d0"]
+
+
+def test_read_and_create_indices_wiring(tmp_path, monkeypatch):
+    """store + index wiring (modeling/util.py:73-108) - construction only, no compute."""
+    from mfar_b200 import resolve_fields
+    from mfar_b200.data import index as index_mod
+    from mfar_b200.modeling import util
+
+    class Enc:
+        def get_sentence_embedding_dimension(self):
+            return 32
+    corpus = tmp_path / "corpus.tsv"
+    corpus.write_text("".join(f"doc{i}\t{json.dumps({'title': 't%d' % i})}\n" for i in range(5)))
+    fields = resolve_fields("title_dense,brand_dense,title_sparse", "amazon")
+    # device="cuda" string is accepted without touching the GPU at construction time
+    c, vd, idx = util.read_and_create_indices(str(corpus), "amazon", fields, str(tmp_path / "vec"), Enc())
+    assert [k for k, _ in c] == [f"doc{i}" for i in range(5)]
+    assert list(idx) == ["brand_dense", "title_dense", "title_sparse"]
+    assert os.path.getsize(tmp_path / "vec" / "title.npy") == 5 * 32 * 4      # file named by field.name
+    assert isinstance(idx["title_dense"], index_mod.DenseFlatIndex)
+    assert isinstance(idx["title_sparse"], index_mod.PrecomputedSparseIndex)
+    vd["title_dense"]["doc2"] = np.ones(32, np.float32)
+    assert vd["title_dense"].file[2].sum() == 32
+
+
+def test_key_packing_roundtrip_and_order():
+    from mfar_b200.dist import decode_keys, encode_keys
+    s = np.array([3.5, -1.25, 0.0, -0.0, 1e-30, -1e30, 3.5], np.float32)
+    i = np.array([7, 1, 2, 3, 4, 5, 6], np.int64)
+    k = encode_keys(s, i)
+    ds, di = decode_keys(k)
+    assert (di == i).all() and (ds == s).all()
+    order = np.argsort(-k.astype(np.float64), kind="stable")        # coarse check via exact uint compare below
+    srt = sorted(range(len(k)), key=lambda j: int(k[j]), reverse=True)
+    # score desc, then id asc: (3.5,6) before (3.5,7)
+    assert srt[:2] == [6, 0] and srt[-1] == 5
+    es, ei = decode_keys(np.zeros(2, np.uint64))
+    assert np.isneginf(es).all() and (ei == -1).all()
+
+
+def test_shard_range_partitions_exactly():
+    from mfar_b200.dist import shard_range
+    for n in (1, 7, 128, 957192, 10_000_000):
+        for w in (1, 2, 4, 8):
+            r = [shard_range(n, i, w) for i in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+def test_qres_line_format():
+    from mfar_b200.data.trec import QRes
+    line = str(QRes("q1", "d9", 0.5))
+    assert line == "q1\t0\td9\t0\t0.5\t0"
+    assert QRes.from_str(line).doc_id == "d9"
