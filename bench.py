@@ -277,6 +277,9 @@ def main():
             nv.check(nv.lib().mfar_profile_enable(1))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
+        ncu_range = profile and os.environ.get("MFAR_NCU_RANGE") == "1"   # ncu --profile-from-start off
+        if ncu_range:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(steps):
             qv, qe, sp = pool[i % len(pool)]
@@ -284,6 +287,8 @@ def main():
             launches += retr.last_launches + 1 + 1          # + mixture-weights kernel + cross-shard merge kernel
         e1.record()
         barrier()
+        if ncu_range:
+            torch.cuda.profiler.stop()
         ms = e0.elapsed_time(e1)
         kern_ms = []
         if profile:

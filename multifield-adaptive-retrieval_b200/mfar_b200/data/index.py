@@ -83,7 +83,9 @@ class DenseFlatIndex(Index[str, str]):
         return self.model.encode(list(queries), convert_to_tensor=True)   # index.py:187
 
     def retrieve(self, query, top_k: int):
-        return self.retrieve_batch([query], top_k)[0]
+        if isinstance(query, np.ndarray) or torch.is_tensor(query):   # a pre-encoded vector [d] or [1,d]
+            return self.retrieve_batch(query.reshape(1, -1), top_k)[0]
+        return self.retrieve_batch([query], top_k)[0]                 # index.py:178-179
 
     def retrieve_batch(self, queries, top_k: int) -> List[List[Tuple[str, float]]]:
         r = self._ensure()

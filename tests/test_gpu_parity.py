@@ -32,7 +32,7 @@ def load(path):
     return z, json.loads(str(z["meta"]))
 
 
-def build(fields, W, query_cond, n_sparse=0, k=100, normalize=False, doc_id_base=0, impl="auto"):
+def build(fields, W, query_cond, n_sparse=0, k=100, normalize=False, doc_id_base=0, impl="auto", n_docs=None):
     MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
     pc = PackedCorpus.from_fields(fields, DEV, normalize) if len(fields) else None
     F = len(fields) + n_sparse
@@ -40,7 +40,7 @@ def build(fields, W, query_cond, n_sparse=0, k=100, normalize=False, doc_id_base
     with torch.no_grad():
         layer.weight.copy_(torch.as_tensor(W))
     layer = layer.to(DEV)
-    n_docs = fields[0].shape[0] if len(fields) else None
+    n_docs = fields[0].shape[0] if len(fields) else n_docs
     return MultiFieldRetriever(pc, layer, n_sparse=n_sparse, top_k=k, doc_id_base=doc_id_base, impl=impl,
                                n_docs=n_docs, device=DEV)
 
@@ -148,9 +148,7 @@ def test_exhaustive_search_vs_oracle(shape, impl):
     if impl == "tcgen05" and Fd == 0:
         pytest.skip("sparse-only batches have no dense contraction: SIMT path by design")
     fields, q, sp, W = synth(seed, N, d, Fd, Fs, Q, qc)
-    r = build(fields, W, qc, Fs, k, impl=impl) if Fd else build([], W, qc, Fs, k, impl=impl)
-    if not Fd:
-        r.n_docs = N
+    r = build(fields, W, qc, Fs, k, impl=impl, n_docs=N)
     mask = torch.ones(Fd + Fs, 1)
     if Fd + Fs > 2:
         mask[1] = 0
