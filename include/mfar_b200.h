@@ -52,9 +52,10 @@ typedef enum mfar_dtype { MFAR_F32 = 0, MFAR_BF16 = 1, MFAR_F16 = 2 } mfar_dtype
 
 /* which scoring kernel mfar_score_topk runs */
 typedef enum mfar_impl {
-  MFAR_IMPL_AUTO = 0,   /* tcgen05 path whenever its shape constraints hold          */
+  MFAR_IMPL_AUTO = 0,   /* tensor-core paths whenever their shape constraints hold; QS for Q > 64 */
   MFAR_IMPL_SIMT = 1,   /* CUDA-core streaming path (small query batches, cross-check) */
-  MFAR_IMPL_TCGEN05 = 2 /* TMA + tcgen05.mma + TMEM path                              */
+  MFAR_IMPL_TCGEN05 = 2, /* TMA + tcgen05.mma + TMEM, docs on the MMA M axis (small/medium batches)  */
+  MFAR_IMPL_TCGEN05_QS = 3 /* query-stationary: queries resident in TMEM, CTA pairs (large batches) */
 } mfar_impl;
 
 MFAR_API int mfar_abi_version(void);

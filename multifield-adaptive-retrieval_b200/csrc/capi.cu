@@ -30,18 +30,29 @@ static int check_arch() {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Geometry {
-  int impl;       // resolved: MFAR_IMPL_SIMT or MFAR_IMPL_TCGEN05
+  int impl;       // resolved: MFAR_IMPL_SIMT, MFAR_IMPL_TCGEN05 or MFAR_IMPL_TCGEN05_QS
   int workers;
   int q_tiles;
-  int q_pad;      // per tile (tc) or total (simt)
+  int q_pad;      // per tile (tc, qs) or total (simt)
   int q_pad_total;
+  int cg;         // qs: CTAs per MMA group (1 or 2)
 };
+
+constexpr int kQsMinBatch = 65;   // AUTO: batches above 64 queries take the query-stationary kernel
 
 static Geometry resolve_geometry(const ScoreArgs& a, int impl) {
   Geometry g{};
-  if (impl == MFAR_IMPL_AUTO) impl = score_tc_supported(a) ? MFAR_IMPL_TCGEN05 : MFAR_IMPL_SIMT;
+  if (impl == MFAR_IMPL_AUTO) {
+    if (a.Q >= kQsMinBatch && score_qs_supported(a)) impl = MFAR_IMPL_TCGEN05_QS;
+    else impl = score_tc_supported(a) ? MFAR_IMPL_TCGEN05 : MFAR_IMPL_SIMT;
+  }
   g.impl = impl;
-  if (impl == MFAR_IMPL_TCGEN05) {
+  g.cg = 1;
+  if (impl == MFAR_IMPL_TCGEN05_QS) {
+    score_qs_geometry(a.Q, a.n_tiles, &g.q_tiles, &g.workers, &g.cg);
+    g.q_pad = 128;
+    g.q_pad_total = g.q_pad * g.q_tiles;
+  } else if (impl == MFAR_IMPL_TCGEN05) {
     score_tc_geometry(a.Q, a.n_tiles, &g.q_pad, &g.q_tiles, &g.workers);
     g.q_pad_total = g.q_pad * g.q_tiles;
   } else {
@@ -130,8 +141,13 @@ size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_spars
     score_simt_geometry(Q, std::max(n_tiles, 1), &qp, &w);
     best = std::max(best, topk_workspace_bytes(w, qp));
   }
+  {
+    int qt, w, cg;
+    score_qs_geometry(Q, std::max(n_tiles, 1), &qt, &w, &cg);
+    best = std::max(best, topk_workspace_bytes(w, qt * 128));
+  }
   size_t total = align_up(best, 256);
-  if (n_sparse > 0) total += align_up(size_t(Q) * size_t(align_up(size_t(n_docs), 4)) * 4, 256);
+  if (n_sparse > 0) total += align_up(size_t(Q) * size_t(align_up(size_t(n_docs), kTileDocs)) * 4, 256);
   return total;
 }
 
@@ -148,7 +164,7 @@ int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int f
   if (n_sparse > 0 && (!sparse || sparse_ld < n_docs)) return MFAR_ERR_ARG;
   if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
   if (doc_id_base < 0 || doc_id_base + n_docs > (int64_t(1) << 32)) return MFAR_ERR_SHAPE;
-  if (impl < MFAR_IMPL_AUTO || impl > MFAR_IMPL_TCGEN05) return MFAR_ERR_ARG;
+  if (impl < MFAR_IMPL_AUTO || impl > MFAR_IMPL_TCGEN05_QS) return MFAR_ERR_ARG;
   if (int rc = check_arch()) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -157,10 +173,11 @@ int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int f
   a.corpus_fields = corpus_fields; a.field_begin = field_begin; a.n_dense = n_dense; a.dim = dim;
   a.q_vecs = q_vecs; a.Q = Q; a.w = w; a.w_ld = n_dense + n_sparse; a.doc_id_base = doc_id_base; a.k = k;
   if (impl == MFAR_IMPL_TCGEN05 && !score_tc_supported(a)) return MFAR_ERR_SHAPE;
+  if (impl == MFAR_IMPL_TCGEN05_QS && !score_qs_supported(a)) return MFAR_ERR_SHAPE;
   const Geometry g = resolve_geometry(a, impl);
 
   const size_t ws_topk = align_up(topk_workspace_bytes(g.workers, g.q_pad_total), 256);
-  const int64_t base_ld = int64_t(align_up(size_t(n_docs), 4));
+  const int64_t base_ld = int64_t(align_up(size_t(n_docs), kTileDocs));   // tile-wide vector reads stay in bounds
   const size_t ws_base = n_sparse > 0 ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
   if (workspace_bytes < ws_topk + ws_base) return MFAR_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MFAR_ERR_ARG;
@@ -177,7 +194,9 @@ int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int f
   int rc;
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][0], st));
-  if (g.impl == MFAR_IMPL_TCGEN05)
+  if (g.impl == MFAR_IMPL_TCGEN05_QS)
+    rc = launch_score_qs(a, workspace, g.workers, g.q_tiles, g.cg, st);
+  else if (g.impl == MFAR_IMPL_TCGEN05)
     rc = launch_score_tc(a, workspace, g.workers, g.q_tiles, g.q_pad, st);
   else
     rc = launch_score_simt(a, workspace, g.workers, g.q_pad, st);

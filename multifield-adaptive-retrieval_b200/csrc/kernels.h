@@ -46,6 +46,10 @@ struct ScoreArgs {
 int launch_score_simt(const ScoreArgs& a, void* ws_base, int workers, int q_pad, cudaStream_t st);
 // TMA + tcgen05 scoring pass.
 int launch_score_tc(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int q_pad, cudaStream_t st);
+// Query-stationary tcgen05 pass for large batches (queries resident in TMEM, CTA pairs when cg == 2).
+int launch_score_qs(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int cg, cudaStream_t st);
+bool score_qs_supported(const ScoreArgs& a);
+void score_qs_geometry(int Q, int n_tiles, int* q_tiles, int* workers, int* cg);
 // Shape envelope of the tcgen05 path.
 bool score_tc_supported(const ScoreArgs& a);
 // geometry chosen for (Q): q_pad per tile, number of q tiles, workers

@@ -1,0 +1,328 @@
+// Query-stationary fused multi-field scoring + streaming top-k for LARGE query batches (sm_100a).
+//
+//   score[q, n] = sum_f w[q,f] * <q_vec[q], corpus[n, f, :]>  (+ base[q, n])  ->  per-CTA top-k
+//
+// Why a second tensor-core kernel: with docs on the UMMA M axis (score_tc.cu) a CTA can keep at most 64
+// queries resident in shared memory next to the corpus ring, so Q=512 re-streams the corpus 8x through L2
+// and the M=128 x N=64 SS-MMAs need 192 B/cycle of shared-memory reads (port: 128 B/cycle) - ncu round 1:
+// tensor pipe 18 % active, DRAM 4.3x the algorithmic bytes.  Here the roles are swapped:
+//
+//   A  = 128 QUERIES per CTA, bf16, resident in TENSOR MEMORY for the whole kernel
+//        (lane = query, dim/2 columns: 384 of the 512 columns at d=768) -> no shared-memory reads for A
+//   B  = 64 docs x 64 K-elements (8 KB, SWIZZLE_128B) streamed by TMA through a deep shared-memory ring
+//   D  = [128 queries x 64 docs] fp32 in the remaining 128 TMEM columns, double buffered
+//   CG = 2: CTA pairs (cta_group::2, M = 256 queries): each CTA TMA-loads HALF of every doc tile and the
+//        pair's tensor cores share it - L2->SM traffic and shared-memory reads per SM are halved.
+//
+// Epilogue orientation: TMEM lane = query, so an epilogue THREAD owns one query: its field weights, its
+// running mixture accumulators (64 docs), its top-k admission threshold and its candidate list - the
+// threshold test is a register compare, no shared-memory traffic, no atomics.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over doc tiles): warp 0 TMA producer, warp 1 TMEM
+// allocator + MMA issuer (leader CTA only when CG = 2), warps 2..5 epilogue.
+// grid = (q_tiles, workers): CTAs with the same blockIdx.y walk the same doc tiles for different query
+// tiles (adjacent in launch order -> co-resident in time, so re-reads hit L2).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace mfar {
+
+constexpr int kQsThreads = 192;
+constexpr int kQsQ = 128;        // queries per CTA (TMEM lanes)
+constexpr int kQsDocs = 64;      // docs per unit (UMMA N)
+constexpr int kQsTmemCols = 512;
+constexpr int kQsDCol = 384;     // accumulator columns start here (A occupies [0, dim/2) <= 384)
+
+struct QsParams {
+  int64_t n_docs;
+  int n_tiles, corpus_fields, field_begin, n_dense, k_chunks;
+  const __nv_bfloat16* q_vecs;
+  int dim;
+  int Q;
+  const float* w;
+  int w_ld;
+  const float* base;
+  int64_t base_ld;
+  int64_t doc_id_base;
+  int k;
+  int stages;
+  TopkWorkspace ws;
+};
+
+template <int CG>
+__global__ void __launch_bounds__(kQsThreads, 1)
+score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
+  constexpr int kRowsPerCta = kQsDocs / CG;               // doc rows this CTA loads per stage
+  constexpr int kStageBytes = kRowsPerCta * kChunkK * 2;  // 8 KB (CG=1) / 4 KB (CG=2)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = smem;
+  float* w_s = reinterpret_cast<float*>(smem_b + size_t(p.stages) * kStageBytes);      // [n_dense][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + size_t(p.n_dense) * kQsQ);
+  uint64_t* full_bar = bars;                       // [stages]  (leader's are the ones waited on)
+  uint64_t* empty_bar = bars + p.stages;           // [stages]
+  uint64_t* tfull_bar = bars + 2 * p.stages;       // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]       (leader's are the ones waited on)
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.y;                        // worker: walks tiles g, g+G, ...
+  const int G = gridDim.y;
+  const int q0 = blockIdx.x * kQsQ;                // first query of this CTA
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  int* err = p.ws.err;
+
+  // ---- one-time setup
+  for (int i = threadIdx.x; i < p.n_dense * kQsQ; i += kQsThreads) {
+    const int f = i / kQsQ, c = i % kQsQ;
+    w_s[i] = (q0 + c < p.Q) ? p.w[int64_t(q0 + c) * p.w_ld + f] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4 * CG); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (CG == 2) { tmem_alloc_cg2(tmem_ptr_s, kQsTmemCols); tmem_relinquish_cg2(); }
+    else { tmem_alloc(tmem_ptr_s, kQsTmemCols); tmem_relinquish(); }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  // ---- queries -> tensor memory (A operand): lane = query, column c holds elements 2c, 2c+1
+  if (warp >= 2) {
+    const int lane_grp = warp & 3;
+    const int qrow = q0 + lane_grp * 32 + lane;
+    const uint4* src = reinterpret_cast<const uint4*>(p.q_vecs + int64_t(qrow) * p.dim);
+    const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16);
+    for (int c0 = 0; c0 < p.dim / 2; c0 += 16) {   // 16 columns = 32 bf16 = 4 x 16-byte loads
+      uint32_t v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 x = make_uint4(0, 0, 0, 0);
+        if (qrow < p.Q) x = __ldg(src + c0 / 4 + j);
+        v[4 * j + 0] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+      }
+      tmem_st16(taddr + c0, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+  const int my_tiles = (p.n_tiles > g) ? (p.n_tiles - g + G - 1) / G : 0;
+  const int units = my_tiles * 2 * p.n_dense;      // (tile, half, field)
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (every CTA)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int t = g + i * G;
+        for (int h = 0; h < 2; ++h) {
+          for (int f = 0; f < p.n_dense; ++f) {
+            const int row0 = (t * p.corpus_fields + p.field_begin + f) * kTileDocs + h * kQsDocs +
+                             int(cta_rank) * kRowsPerCta;
+            for (int kc = 0; kc < p.k_chunks; ++kc) {
+              mbar_wait(&empty_bar[stage], phase ^ 1, err, 11);
+              if (CG == 2) {
+                if (leader) mbar_expect_tx(&full_bar[stage], kStageBytes * 2);
+                tma_load_2d_cg2(&map_b, &full_bar[stage], smem_b + size_t(stage) * kStageBytes, kc * kChunkK, row0);
+              } else {
+                mbar_expect_tx(&full_bar[stage], kStageBytes);
+                tma_load_2d(&map_b, &full_bar[stage], smem_b + size_t(stage) * kStageBytes, kc * kChunkK, row0);
+              }
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(kQsQ * CG, kQsDocs);
+      int stage = 0; uint32_t phase = 0;
+      for (int u = 0; u < units; ++u) {
+        const int buf = u & 1;
+        mbar_wait(&tempty_bar[buf], ((u >> 1) & 1) ^ 1, err, 13);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(kQsDCol + buf * kQsDocs);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase, err, 14);
+          tc_fence_after();
+          const uint64_t b_desc = make_sw128_desc(smem_u32(smem_b + size_t(stage) * kStageBytes));
+#pragma unroll
+          for (int kk = 0; kk < kChunkK / kUmmaK; ++kk) {
+            const uint32_t a_tmem = tmem_base + uint32_t(kc * (kChunkK / 2) + kk * (kUmmaK / 2));
+            if (CG == 2) umma_bf16_ts_cg2(d_tmem, a_tmem, b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+            else umma_bf16_ts(d_tmem, a_tmem, b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+          }
+          if (CG == 2) tc_commit_cg2(&empty_bar[stage], 0x3); else tc_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (CG == 2) tc_commit_cg2(&tfull_bar[buf], 0x3); else tc_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue: thread = query
+    const int lane_grp = warp & 3;
+    const int qloc = lane_grp * 32 + lane;
+    const int qrow = q0 + qloc;
+    const bool q_valid = qrow < p.Q;
+    uint64_t* my_list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + qrow) * kCandCap;
+    const float* my_base = p.base ? p.base + int64_t(q_valid ? qrow : 0) * p.base_ld : nullptr;
+    uint64_t thr = 0ull;
+    int cnt = 0;
+    float acc[kQsDocs];
+    int u = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int t = g + i * G;
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int c = 0; c < kQsDocs; ++c) acc[c] = 0.f;
+        for (int f = 0; f < p.n_dense; ++f, ++u) {
+          const int buf = u & 1;
+          mbar_wait(&tfull_bar[buf], (u >> 1) & 1, err, 15);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(kQsDCol + buf * kQsDocs);
+          const float wf = w_s[f * kQsQ + qloc];
+#pragma unroll
+          for (int c0 = 0; c0 < kQsDocs; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc[c0 + c] = fmaf(wf, __uint_as_float(v[c]), acc[c0 + c]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {                           // one arrival per epilogue warp frees the accumulator buffer
+            if (CG == 2) mbar_arrive_cluster_rank0(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
+          }
+        }
+        // ---- 64 docs scored under every field: + pre-mixed sparse term, threshold filter, push
+        const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
+        if (q_valid && doc0 < p.n_docs) {
+          const int64_t left = p.n_docs - doc0;
+          const int nd = left < kQsDocs ? int(left) : kQsDocs;
+          if (my_base) {
+            const float4* b4 = reinterpret_cast<const float4*>(my_base + doc0);
+#pragma unroll
+            for (int c = 0; c < kQsDocs; c += 4) {
+              const float4 b = __ldg(b4 + c / 4);
+              acc[c] += b.x; acc[c + 1] += b.y; acc[c + 2] += b.z; acc[c + 3] += b.w;
+            }
+          }
+          const uint32_t id0 = uint32_t(p.doc_id_base + doc0);
+#pragma unroll
+          for (int c = 0; c < kQsDocs; ++c) {
+            const uint64_t key = make_key(acc[c], id0 + c);
+            if (c < nd && key > thr) { __stcg(my_list + cnt, key); ++cnt; }
+          }
+        }
+        // ---- lists that could overflow on the next unit are compacted by the whole warp, one at a time
+        unsigned need = __ballot_sync(0xffffffffu, cnt > kCandCap - kQsDocs);
+        while (need) {
+          const int l = __ffs(need) - 1;
+          need &= need - 1;
+          const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
+          uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
+          __syncwarp();
+          const uint64_t kth = warp_compact_list(list_l, cnt_l, p.k, lane);
+          if (lane == l) { thr = kth; cnt = p.k; }
+          __syncwarp();
+        }
+      }
+    }
+    if (q_valid) {
+      p.ws.cand_cnt[int64_t(g) * p.ws.q_pad + qrow] = cnt;
+      p.ws.cand_thr[int64_t(g) * p.ws.q_pad + qrow] = thr;
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, kQsTmemCols); else tmem_dealloc(tmem_base, kQsTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+bool score_qs_supported(const ScoreArgs& a) {
+  return a.n_dense >= 1 && a.dim % kChunkK == 0 && a.dim >= kChunkK && a.dim / 2 <= kQsDCol &&
+         (reinterpret_cast<uintptr_t>(a.corpus) % 16 == 0) && (reinterpret_cast<uintptr_t>(a.q_vecs) % 16 == 0) &&
+         int64_t(a.n_tiles) * a.corpus_fields * kTileDocs < (int64_t(1) << 31);
+}
+
+void score_qs_geometry(int Q, int n_tiles, int* q_tiles, int* workers, int* cg) {
+  int qt = (Q + kQsQ - 1) / kQsQ;
+  const int c = qt >= 2 ? 2 : 1;
+  qt = round_up(qt, c);
+  int w = kNumSmsB200 / qt;
+  if (w > n_tiles) w = n_tiles;
+  if (w < 1) w = 1;
+  *q_tiles = qt; *workers = w; *cg = c;
+}
+
+static size_t qs_smem_bytes(int n_dense, int stages, int stage_bytes) {
+  return 1024 + size_t(stages) * stage_bytes + size_t(n_dense) * kQsQ * 4 + (2 * stages + 4) * 8 + 16;
+}
+
+template <int CG>
+static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, cudaStream_t st) {
+  constexpr int kStageBytes = (kQsDocs / CG) * kChunkK * 2;
+  QsParams p;
+  p.n_docs = a.n_docs; p.n_tiles = a.n_tiles; p.corpus_fields = a.corpus_fields; p.field_begin = a.field_begin;
+  p.n_dense = a.n_dense; p.k_chunks = a.dim / kChunkK; p.q_vecs = static_cast<const __nv_bfloat16*>(a.q_vecs);
+  p.dim = a.dim; p.Q = a.Q; p.w = a.w; p.w_ld = a.w_ld; p.base = a.base; p.base_ld = a.base_ld;
+  p.doc_id_base = a.doc_id_base; p.k = a.k;
+  p.ws = carve_workspace(ws_base, workers, q_tiles * kQsQ);
+  const size_t smem_cap = 227 * 1024;
+  int stages = CG == 2 ? 40 : 24;
+  while (stages > 2 && qs_smem_bytes(a.n_dense, stages, kStageBytes) > smem_cap) --stages;
+  p.stages = stages;
+  const size_t smem = qs_smem_bytes(a.n_dense, stages, kStageBytes);
+  if (smem > smem_cap) return MFAR_ERR_SHAPE;
+
+  CUtensorMap map_b;
+  int rc = make_tensor_map_2d(&map_b, a.corpus, uint64_t(a.n_tiles) * a.corpus_fields * kTileDocs, a.dim,
+                              kQsDocs / CG, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc) return rc;
+  static bool attr_set = false;   // per template instantiation
+  if (!attr_set) {
+    MFAR_CUDA_OK(cudaFuncSetAttribute(score_qs_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(q_tiles, workers);
+  cfg.blockDim = dim3(kQsThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MFAR_CUDA_OK(cudaLaunchKernelEx(&cfg, score_qs_kernel<CG>, map_b, p));
+  return MFAR_OK;
+}
+
+int launch_score_qs(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int cg, cudaStream_t st) {
+  if (!score_qs_supported(a)) return MFAR_ERR_SHAPE;
+  if (cg == 2) return launch_qs_impl<2>(a, ws_base, workers, q_tiles, st);
+  return launch_qs_impl<1>(a, ws_base, workers, q_tiles, st);
+}
+
+}  // namespace mfar

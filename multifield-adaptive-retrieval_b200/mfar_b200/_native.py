@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmfar_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
-IMPL = {"auto": 0, "simt": 1, "tcgen05": 2}
+IMPL = {"auto": 0, "simt": 1, "tcgen05": 2, "tcgen05_qs": 3}
 TILE_DOCS = 128
 MAX_K = 128
 MAX_FIELDS = 64

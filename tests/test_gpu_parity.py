@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
-IMPLS = ["simt", "tcgen05"]
+IMPLS = ["simt", "tcgen05", "tcgen05_qs"]
 DEV = "cuda"
 
 
@@ -138,6 +138,8 @@ SHAPES = [
     (27, 129, 64, 2, 1, 17, True, 100),         # 2 tiles, the second with a single doc
     (28, 128, 128, 4, 0, 33, True, 128),        # k = 128 = N (everything returned)
     (29, 5000, 256, 2, 0, 130, True, 10),       # three query tiles
+    (30, 4000, 768, 3, 1, 200, True, 100),      # large batch, hybrid: CTA-pair query-stationary path under auto
+    (31, 2500, 768, 2, 0, 300, False, 100),     # 3 query tiles of 128 -> padded to 2 pairs
 ]
 
 
@@ -145,7 +147,7 @@ SHAPES = [
 @pytest.mark.parametrize("shape", SHAPES, ids=[f"s{s[0]}" for s in SHAPES])
 def test_exhaustive_search_vs_oracle(shape, impl):
     seed, N, d, Fd, Fs, Q, qc, k = shape
-    if impl == "tcgen05" and Fd == 0:
+    if impl != "simt" and Fd == 0:
         pytest.skip("sparse-only batches have no dense contraction: SIMT path by design")
     fields, q, sp, W = synth(seed, N, d, Fd, Fs, Q, qc)
     r = build(fields, W, qc, Fs, k, impl=impl, n_docs=N)
@@ -189,6 +191,28 @@ def test_simt_and_tcgen05_agree_at_scale():
     w = O.mixture_weights(q.float().cpu(), layer.weight.cpu(), True)[0]
     ref = sum(w[f] * (per_field[f] @ q[0].float().cpu()) for f in range(F))
     torch.testing.assert_close(s2[0].cpu(), ref, rtol=2e-5, atol=1e-4)
+
+
+def test_query_stationary_agrees_with_doc_stationary_at_scale():
+    """Large-batch kernel (queries in TMEM, CTA pairs) vs the doc-stationary tcgen05 kernel over 150k docs x 3
+    fields at Q=384: same ids except near-ties, same scores."""
+    MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    from mfar_b200 import synth as S
+    N, F, d, Q, k = 150_000, 3, 768, 384, 100
+    pc = PackedCorpus(N, F, d, DEV)
+    S.fill_packed_corpus(pc, seed=17)
+    mu = S.corpus_mean(d, 17, DEV)
+    q = S.make_queries(Q, d, mu, 18, DEV)
+    layer = LinearWeights(d, F, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(S.make_mixture(d, F, 19))
+    r = MultiFieldRetriever(pc, layer.to(DEV), top_k=k)
+    s1, i1 = r.search(q, q.float(), impl="tcgen05")
+    s2, i2 = r.search(q, q.float(), impl="tcgen05_qs")
+    assert (s2[:, :-1] >= s2[:, 1:]).all()
+    assert all(len(set(row.tolist())) == k for row in i2.cpu())
+    torch.testing.assert_close(s1, s2, rtol=2e-5, atol=1e-4)
+    assert (i1 == i2).float().mean().item() > 0.98
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])

@@ -45,8 +45,12 @@ def probe(N, d, F, Q, impl, seed=0):
 if __name__ == "__main__":
     ok = True
     for impl in sys.argv[1:] or ["simt", "tcgen05"]:
-        for (N, d, F, Q) in [(128, 64, 1, 1), (128, 64, 1, 16), (128, 128, 1, 16), (128, 768, 1, 16),
-                             (128, 768, 2, 16), (256, 768, 3, 40), (1000, 768, 4, 64), (5000, 768, 8, 3)]:
+        shapes = [(128, 64, 1, 1), (128, 64, 1, 16), (128, 128, 1, 16), (128, 768, 1, 16),
+                  (128, 768, 2, 16), (256, 768, 3, 40), (1000, 768, 4, 64), (5000, 768, 8, 3)]
+        if impl == "tcgen05_qs":
+            shapes += [(128, 64, 1, 128), (1000, 768, 2, 100), (128, 64, 1, 130), (128, 768, 1, 256),
+                       (3000, 768, 3, 256), (40000, 768, 8, 512), (20000, 768, 2, 700)]
+        for (N, d, F, Q) in shapes:
             try:
                 ok &= probe(N, d, F, Q, impl)
             except Exception as e:  # noqa: BLE001
