@@ -9,7 +9,9 @@
 //
 //   A  = 128 QUERIES per CTA, bf16, resident in TENSOR MEMORY for the whole kernel
 //        (lane = query, dim/2 columns: 384 of the 512 columns at d=768) -> no shared-memory reads for A
-//   B  = 64 docs x 64 K-elements (8 KB, SWIZZLE_128B) streamed by TMA through a deep shared-memory ring
+//   B  = 64 docs x (KC x 64) K-elements per stage (up to 48 KB, SWIZZLE_128B), ONE 3-D TMA box per stage: the
+//        tensor map views a corpus row as [dim/64 chunks][64], so a box lands as KC consecutive [rows x 128 B]
+//        K-major blocks - one mbarrier round trip and one tcgen05.commit per 4*KC MMAs instead of per 4
 //   D  = [128 queries x 64 docs] fp32 in the remaining 128 TMEM columns, double buffered
 //   CG = 2: CTA pairs (cta_group::2, M = 256 queries): each CTA TMA-loads HALF of every doc tile and the
 //        pair's tensor cores share it - L2->SM traffic and shared-memory reads per SM are halved.
@@ -18,8 +20,9 @@
 // running mixture accumulators (64 docs), its top-k admission threshold and its candidate list - the
 // threshold test is a register compare, no shared-memory traffic, no atomics.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over doc tiles): warp 0 TMA producer, warp 1 TMEM
-// allocator + MMA issuer (leader CTA only when CG = 2), warps 2..5 epilogue.
+// Warp roles (224 threads, 1 CTA / SM, persistent over doc tiles): warp 0 TMA producer, warp 1 TMEM
+// allocator + MMA issuer for even units, warp 6 MMA issuer for odd units (leader CTA only when CG = 2),
+// warps 2..5 epilogue.
 // grid = (q_tiles, workers): CTAs with the same blockIdx.y walk the same doc tiles for different query
 // tiles (adjacent in launch order -> co-resident in time, so re-reads hit L2).
 #include <cuda.h>
@@ -30,7 +33,8 @@
 
 namespace mfar {
 
-constexpr int kQsThreads = 192;
+constexpr int kQsThreads = 224;
+constexpr int kQsIssuerBWarp = 6;   // second MMA-issuing warp (odd units)
 constexpr int kQsQ = 128;        // queries per CTA (TMEM lanes)
 constexpr int kQsDocs = 64;      // docs per unit (UMMA N)
 constexpr int kQsTmemCols = 512;
@@ -48,7 +52,8 @@ struct QsParams {
   int64_t base_ld;
   int64_t doc_id_base;
   int k;
-  int stages;
+  int stages;          // ring depth
+  int kc_per_stage;    // 64-element K chunks per stage (divides k_chunks)
   TopkWorkspace ws;
 };
 
@@ -56,7 +61,9 @@ template <int CG>
 __global__ void __launch_bounds__(kQsThreads, 1)
 score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
   constexpr int kRowsPerCta = kQsDocs / CG;               // doc rows this CTA loads per stage
-  constexpr int kStageBytes = kRowsPerCta * kChunkK * 2;  // 8 KB (CG=1) / 4 KB (CG=2)
+  constexpr int kChunkBytes = kRowsPerCta * kChunkK * 2;  // one [rows x 64] K-major block: 8 KB (CG=1) / 4 KB (CG=2)
+  const int kStageBytes = p.kc_per_stage * kChunkBytes;
+  const int stages_per_unit = p.k_chunks / p.kc_per_stage;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;
@@ -94,10 +101,18 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_s;
+  // The whole tensor memory (512 columns) is allocated, so the allocation can only start at lane 0 / column 0.
+  // Using the literal keeps every TMEM address of the MMA issue loop in uniform registers (no per-instruction
+  // R2UR of a value loaded from shared memory); anything else is a driver/hardware surprise -> trap.
+  if (*tmem_ptr_s != 0u) {
+    if (threadIdx.x == 0) atomicExch(err, 21);
+    __threadfence_system();
+    asm volatile("trap;");
+  }
+  constexpr uint32_t tmem_base = 0u;
 
   // ---- queries -> tensor memory (A operand): lane = query, column c holds elements 2c, 2c+1
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int lane_grp = warp & 3;
     const int qrow = q0 + lane_grp * 32 + lane;
     const uint4* src = reinterpret_cast<const uint4*>(p.q_vecs + int64_t(qrow) * p.dim);
@@ -123,7 +138,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
 
   if (warp == 0) {
     // ===================================================================== TMA producer (every CTA)
-    if (lane == 0) {
+    {                                               // whole warp walks the loop, one elected lane issues
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int t = g + i * G;
@@ -131,45 +146,64 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           for (int f = 0; f < p.n_dense; ++f) {
             const int row0 = (t * p.corpus_fields + p.field_begin + f) * kTileDocs + h * kQsDocs +
                              int(cta_rank) * kRowsPerCta;
-            for (int kc = 0; kc < p.k_chunks; ++kc) {
+            for (int s = 0; s < stages_per_unit; ++s) {
               mbar_wait(&empty_bar[stage], phase ^ 1, err, 11);
-              if (CG == 2) {
-                if (leader) mbar_expect_tx(&full_bar[stage], kStageBytes * 2);
-                tma_load_2d_cg2(&map_b, &full_bar[stage], smem_b + size_t(stage) * kStageBytes, kc * kChunkK, row0);
-              } else {
-                mbar_expect_tx(&full_bar[stage], kStageBytes);
-                tma_load_2d(&map_b, &full_bar[stage], smem_b + size_t(stage) * kStageBytes, kc * kChunkK, row0);
+              if (elect_one()) {
+                if (CG == 2) {
+                  if (leader) mbar_expect_tx(&full_bar[stage], kStageBytes * 2);
+                  tma_load_3d_cg2(&map_b, &full_bar[stage], smem_b + size_t(stage) * kStageBytes, 0, row0,
+                                  s * p.kc_per_stage);
+                } else {
+                  mbar_expect_tx(&full_bar[stage], kStageBytes);
+                  tma_load_3d(&map_b, &full_bar[stage], smem_b + size_t(stage) * kStageBytes, 0, row0,
+                              s * p.kc_per_stage);
+                }
               }
+              __syncwarp();
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (leader CTA)
-    if (lane == 0 && leader) {
+  } else if (warp == 1 || warp == kQsIssuerBWarp) {
+    // ===================================================================== MMA issuers (leader CTA)
+    // TWO issuing warps: warp 1 owns the even units (accumulator buffer 0), warp 6 the odd units (buffer 1).
+    // An M=256 x N=64 x K=16 MMA occupies the tensor pipe for 32 cycles but costs a single warp ~65 cycles of
+    // issue work (descriptor arithmetic, elect, uniform-register moves) - measured 3330 cycles per 48-MMA unit
+    // against a 1536-cycle floor.  Two warps feed the in-order tensor pipe from both sides; tcgen05.commit
+    // tracks the issuing thread's own MMAs, so each warp releases exactly the stages / accumulator it consumed.
+    if (leader) {                                   // whole warp walks the loop, one elected lane issues
       constexpr uint32_t idesc = make_idesc(kQsQ * CG, kQsDocs);
-      int stage = 0; uint32_t phase = 0;
-      for (int u = 0; u < units; ++u) {
-        const int buf = u & 1;
+      const int buf = (warp == 1) ? 0 : 1;
+      const uint32_t d_tmem = tmem_base + uint32_t(kQsDCol + buf * kQsDocs);
+      for (int u = buf; u < units; u += 2) {
         mbar_wait(&tempty_bar[buf], ((u >> 1) & 1) ^ 1, err, 13);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(kQsDCol + buf * kQsDocs);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int s = 0; s < stages_per_unit; ++s) {
+          const int ring = u * stages_per_unit + s;   // position in the producer's stage sequence
+          const int stage = ring % p.stages;
+          const uint32_t phase = uint32_t(ring / p.stages) & 1u;
           mbar_wait(&full_bar[stage], phase, err, 14);
           tc_fence_after();
-          const uint64_t b_desc = make_sw128_desc(smem_u32(smem_b + size_t(stage) * kStageBytes));
+          const uint32_t stage_addr = smem_u32(smem_b + size_t(stage) * kStageBytes);
+          for (int c = 0; c < p.kc_per_stage; ++c) {
+            const uint64_t b_desc = make_sw128_desc(stage_addr + uint32_t(c * kChunkBytes));
+            const int kc = s * p.kc_per_stage + c;
 #pragma unroll
-          for (int kk = 0; kk < kChunkK / kUmmaK; ++kk) {
-            const uint32_t a_tmem = tmem_base + uint32_t(kc * (kChunkK / 2) + kk * (kUmmaK / 2));
-            if (CG == 2) umma_bf16_ts_cg2(d_tmem, a_tmem, b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
-            else umma_bf16_ts(d_tmem, a_tmem, b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+            for (int kk = 0; kk < kChunkK / kUmmaK; ++kk) {
+              const uint32_t a_tmem = tmem_base + uint32_t(kc * (kChunkK / 2) + kk * (kUmmaK / 2));
+              if (elect_one()) {
+                if (CG == 2) umma_bf16_ts_cg2(d_tmem, a_tmem, b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+                else umma_bf16_ts(d_tmem, a_tmem, b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+              }
+            }
           }
-          if (CG == 2) tc_commit_cg2(&empty_bar[stage], 0x3); else tc_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          __syncwarp();
+          if (elect_one()) { if (CG == 2) tc_commit_cg2(&empty_bar[stage], 0x3); else tc_commit(&empty_bar[stage]); }
         }
-        if (CG == 2) tc_commit_cg2(&tfull_bar[buf], 0x3); else tc_commit(&tfull_bar[buf]);
+        if (elect_one()) { if (CG == 2) tc_commit_cg2(&tfull_bar[buf], 0x3); else tc_commit(&tfull_bar[buf]); }
+        __syncwarp();
       }
     }
   } else {
@@ -282,7 +316,7 @@ static size_t qs_smem_bytes(int n_dense, int stages, int stage_bytes) {
 
 template <int CG>
 static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, cudaStream_t st) {
-  constexpr int kStageBytes = (kQsDocs / CG) * kChunkK * 2;
+  constexpr int kChunkBytes = (kQsDocs / CG) * kChunkK * 2;
   QsParams p;
   p.n_docs = a.n_docs; p.n_tiles = a.n_tiles; p.corpus_fields = a.corpus_fields; p.field_begin = a.field_begin;
   p.n_dense = a.n_dense; p.k_chunks = a.dim / kChunkK; p.q_vecs = static_cast<const __nv_bfloat16*>(a.q_vecs);
@@ -290,15 +324,20 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   p.doc_id_base = a.doc_id_base; p.k = a.k;
   p.ws = carve_workspace(ws_base, workers, q_tiles * kQsQ);
   const size_t smem_cap = 227 * 1024;
-  int stages = CG == 2 ? 40 : 24;
+  int kc = 1;                                       // largest divisor of k_chunks with a stage <= 48 KB
+  for (int d = 1; d <= p.k_chunks; ++d)
+    if (p.k_chunks % d == 0 && d * kChunkBytes <= 48 * 1024) kc = d;
+  p.kc_per_stage = kc;
+  const int kStageBytes = kc * kChunkBytes;
+  int stages = (192 * 1024) / kStageBytes;
   while (stages > 2 && qs_smem_bytes(a.n_dense, stages, kStageBytes) > smem_cap) --stages;
   p.stages = stages;
   const size_t smem = qs_smem_bytes(a.n_dense, stages, kStageBytes);
   if (smem > smem_cap) return MFAR_ERR_SHAPE;
 
   CUtensorMap map_b;
-  int rc = make_tensor_map_2d(&map_b, a.corpus, uint64_t(a.n_tiles) * a.corpus_fields * kTileDocs, a.dim,
-                              kQsDocs / CG, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  int rc = make_tensor_map_kchunked(&map_b, a.corpus, uint64_t(a.n_tiles) * a.corpus_fields * kTileDocs, a.dim,
+                                    kQsDocs / CG, kc, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) return rc;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {

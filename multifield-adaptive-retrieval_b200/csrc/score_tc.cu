@@ -100,10 +100,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0 && units > 0) {
-      mbar_expect_tx(bq_bar, uint32_t(p.k_chunks) * b_chunk_bytes);
-      for (int kc = 0; kc < p.k_chunks; ++kc)
-        tma_load_2d(&map_b, bq_bar, smem_b + size_t(kc) * b_chunk_bytes, kc * kChunkK, q0);
+    if (units > 0) {                                // whole warp walks the loop, one elected lane issues
+      if (elect_one()) {
+        mbar_expect_tx(bq_bar, uint32_t(p.k_chunks) * b_chunk_bytes);
+        for (int kc = 0; kc < p.k_chunks; ++kc)
+          tma_load_2d(&map_b, bq_bar, smem_b + size_t(kc) * b_chunk_bytes, kc * kChunkK, q0);
+      }
+      __syncwarp();
       int stage = 0; uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int t = g + i * gridDim.x;
@@ -111,8 +114,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const int row0 = (t * p.corpus_fields + p.field_begin + f) * kTileDocs;
           for (int kc = 0; kc < p.k_chunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1, err, 1);
-            mbar_expect_tx(&full_bar[stage], kABytes);
-            tma_load_2d(&map_a, &full_bar[stage], smem_a + size_t(stage) * kABytes, kc * kChunkK, row0);
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[stage], kABytes);
+              tma_load_2d(&map_a, &full_bar[stage], smem_a + size_t(stage) * kABytes, kc * kChunkK, row0);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -120,7 +126,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && units > 0) {
+    if (units > 0) {                                // whole warp walks the loop, one elected lane issues
       constexpr uint32_t idesc = make_idesc(kTileDocs, QP);
       mbar_wait(bq_bar, 0, err, 2);
       tc_fence_after();
@@ -138,12 +144,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int kk = 0; kk < kChunkK / kUmmaK; ++kk) {
             // advance 16 elements = 32 B along K inside the 128 B swizzle span: +2 in the >>4 address field
-            umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+            if (elect_one())
+              umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
           }
-          tc_commit(&empty_bar[stage]);            // smem stage reusable once these MMAs retire
+          __syncwarp();
+          if (elect_one()) tc_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[buf]);                // accumulator of this unit complete
+        if (elect_one()) tc_commit(&tfull_bar[buf]);       // accumulator of this unit complete
+        __syncwarp();
       }
     }
   } else {

@@ -44,6 +44,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     }
   }
 }
+// One lane of a converged warp.  Issue tcgen05 / TMA instructions as `if (elect_one()) asm(...)` from
+// warp-UNIFORM control flow: operands computed outside the `if` stay in uniform registers, so the issuing
+// loop is not slowed by per-instruction vote/R2UR "waterfall" sequences.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -128,6 +140,16 @@ __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* map, uint64_t
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tc_commit_cg2(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
@@ -196,5 +218,26 @@ static inline int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_
   return MFAR_OK;
 }
 
+
+// 3-D "K-chunked" view of a bf16 row-major [rows, cols] tensor: dims (64 | rows | cols/64) with strides
+// (2 B | cols*2 B | 128 B).  A box (64, box_rows, kc) lands in shared memory as kc consecutive
+// [box_rows x 128 B] blocks, each 128-byte swizzled: exactly the K-major SWIZZLE_128B operand layout
+// tcgen05.mma consumes, for kc*64 K-elements, with ONE TMA instruction.
+static inline int make_tensor_map_kchunked(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                                           uint32_t box_rows, uint32_t kc, CUtensorMapL2promotion promo) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MFAR_ERR_CUDA;
+  cuuint64_t gdim[3] = {cuuint64_t(kChunkK), rows, cols / kChunkK};
+  cuuint64_t gstride[2] = {cols * 2, cuuint64_t(kChunkK) * 2};
+  cuuint32_t box[3] = {cuuint32_t(kChunkK), box_rows, kc};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[mfar_b200] cuTensorMapEncodeTiled (k-chunked) failed: %d\n", int(r));
+    return MFAR_ERR_CUDA;
+  }
+  return MFAR_OK;
+}
 
 }  // namespace mfar
