@@ -14,6 +14,9 @@ constexpr int kTileDocs = MFAR_TILE_DOCS;  // docs per corpus tile == UMMA M
 constexpr int kMaxK = MFAR_MAX_K;
 constexpr int kCandCap = 256;              // per-(worker, query) candidate slots; >= kMaxK + kTileDocs
 constexpr int kNumSmsB200 = 148;
+constexpr int kProgressInts = 1024;        // cross-CTA progress counters (score_qs lockstep), one per (worker, query group)
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 #define MFAR_CUDA_OK(expr)                                                                   \
   do {                                                                                       \
@@ -55,21 +58,22 @@ __host__ __device__ __forceinline__ float key_score(uint64_t key) { return order
 __host__ __device__ __forceinline__ uint32_t key_doc(uint64_t key) { return ~uint32_t(key & 0xFFFFFFFFull); }
 
 // Workspace carve-up shared by the scoring kernels and the merge.
-//   cand_keys [G][Qp][kCandCap] u64 | cand_cnt [G][Qp] i32 | cand_thr [G][Qp] u64 | err flag
+//   cand_keys [G][Qp][kCandCap] u64 | cand_thr [G][Qp] u64 | cand_cnt [G][Qp] i32 | err flag (256 B) |
+//   progress counters (kProgressInts i32, zeroed by the launcher of the kernel that uses them)
 struct TopkWorkspace {
   uint64_t* cand_keys;
   int* cand_cnt;
   uint64_t* cand_thr;
   int* err;
+  int* progress;
   int workers;  // G
   int q_pad;    // Qp
 };
 
-__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 inline size_t topk_workspace_bytes(int workers, int q_pad) {
   size_t n = size_t(workers) * q_pad;
-  return n * kCandCap * 8 + n * 8 + n * 4 + 256;
+  return n * kCandCap * 8 + n * 8 + round_up(int(n * 4), 256) + 256 + kProgressInts * 4;
 }
 inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
   TopkWorkspace w;
@@ -78,7 +82,9 @@ inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
   w.cand_keys = reinterpret_cast<uint64_t*>(p); p += n * kCandCap * 8;
   w.cand_thr = reinterpret_cast<uint64_t*>(p);  p += n * 8;
   w.cand_cnt = reinterpret_cast<int*>(p);       p += n * 4;
-  w.err = reinterpret_cast<int*>(p);
+  p += round_up(int(n * 4), 256);
+  w.err = reinterpret_cast<int*>(p);            p += 256;
+  w.progress = reinterpret_cast<int*>(p);
   w.workers = workers;
   w.q_pad = q_pad;
   return w;

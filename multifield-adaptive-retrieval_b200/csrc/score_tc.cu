@@ -68,7 +68,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint64_t* bq_bar = tempty_bar + 2;               // [1]
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bq_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
+  const int lane = threadIdx.x & 31;
   const int g = blockIdx.x;                        // worker (walks tiles g, g+G, ...)
   const int q0 = blockIdx.y * QP;                  // first query of this CTA's tile
   const int nq = min(QP, p.Q - q0);
@@ -128,6 +129,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // ===================================================================== MMA issuer
     if (units > 0) {                                // whole warp walks the loop, one elected lane issues
       constexpr uint32_t idesc = make_idesc(kTileDocs, QP);
+      const uint32_t issue = elect_one() ? 1u : 0u;
       mbar_wait(bq_bar, 0, err, 2);
       tc_fence_after();
       int stage = 0; uint32_t phase = 0;
@@ -144,8 +146,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
           for (int kk = 0; kk < kChunkK / kUmmaK; ++kk) {
             // advance 16 elements = 32 B along K inside the 128 B swizzle span: +2 in the >>4 address field
-            if (elect_one())
-              umma_bf16(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0);
+            umma_bf16_pred(d_tmem, a_desc + uint64_t(kk * 2), b_desc + uint64_t(kk * 2), idesc, (kc | kk) != 0, issue);
           }
           __syncwarp();
           if (elect_one()) tc_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
