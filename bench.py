@@ -196,7 +196,7 @@ def main():
     ap.add_argument("--workload", default="scale_10m_all")
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--docs", type=int, default=0, help="override the workload's doc count (debug)")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_qs"])
     ap.add_argument("--extra-batches", default="1,64", help="also measured on the device-resident path at N=1")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--seed", type=int, default=1234)
@@ -376,7 +376,14 @@ def main():
                     "frac": achieved / peaks["bf16_tflops_sustained"],
                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
                     "hbm_gbs_same_launch": a_bytes / (k_ms * 1e-3) / 1e9}
-        roof.update({"traffic": None, "kernel": "score_tc_kernel" if args.kernel != "simt" else "score_simt_kernel",
+        kname = {"simt": "score_simt_kernel", "tcgen05": "score_tc_kernel", "tcgen05_qs": "score_qs_kernel"}.get(
+            args.kernel, "score_qs_kernel" if Q > 64 else "score_tc_kernel")
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and world == 1 and not args.docs:
+            traffic = json.load(open(tpath)).get(f"{args.workload}|{Q}")
+        roof.update({"traffic": traffic, "traffic_source": "ncu --set full capture, profiles/ncu_traffic.json" if traffic else None,
+                     "kernel": kname,
                      "kernel_ms": k_ms, "kernel_share_of_step": k_ms * len(kern_ms) / ms_total if ms_total else None,
                      "algorithmic_bytes_per_launch": a_bytes, "algorithmic_flops_per_launch": a_flops,
                      "peak_source": peaks["source"] + (" (sustained: kernel timed inside a long step)" if not hbm_bound else " copy bandwidth")})
