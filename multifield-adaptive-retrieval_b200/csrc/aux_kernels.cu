@@ -193,6 +193,47 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
   }
   __syncthreads();
   const int64_t total = int64_t(L) * slots;
+  // ---- fast path: one sync-free sweep with independent (unrolled) loads.  After the threshold filter the survivors
+  // of a many-list merge normally fit the buffer; if they do not, fall through to the streaming path below.
+  {
+    constexpr int kUnroll = 8;
+    for (int64_t base = 0; base < total; base += int64_t(kMergeThreads) * kUnroll) {
+      uint64_t key[kUnroll];
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j) {
+        const int64_t i = base + int64_t(j) * kMergeThreads + t;
+        key[j] = 0ull;
+        if (i < total) {
+          const int l = int(i / slots), sl = int(i % slots);
+          const int cnt = counts ? __ldg(counts + int64_t(l) * q_stride + q) : slots;
+          if (sl < cnt) key[j] = __ldcg(keys + (int64_t(l) * q_stride + q) * slots + sl);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j)
+        if (key[j] != 0ull && key[j] >= s_thr) {
+          const int pos = atomicAdd(&s_cnt, 1);
+          if (pos < kMergeBuf) buf[pos] = key[j];
+        }
+    }
+    __syncthreads();
+    const int c = s_cnt;
+    if (c <= kMergeBuf) {
+      for (int j = c + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
+      block_sort1024_desc(buf);
+      for (int j = t; j < k; j += kMergeThreads) {
+        const uint64_t key = buf[j];
+        if (out_keys) out_keys[int64_t(q) * k + j] = key;
+        if (out_scores) out_scores[int64_t(q) * k + j] = key ? key_score(key) : -INFINITY;
+        if (out_ids) out_ids[int64_t(q) * k + j] = key ? int64_t(key_doc(key)) : int64_t(-1);
+      }
+      return;
+    }
+    __syncthreads();
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+  }
+  // ---- streaming path
   for (int64_t base = 0; base < total; base += kMergeThreads) {
     const int64_t i = base + t;
     if (i < total) {

@@ -59,13 +59,17 @@ __host__ __device__ __forceinline__ uint32_t key_doc(uint64_t key) { return ~uin
 
 // Workspace carve-up shared by the scoring kernels and the merge.
 //   cand_keys [G][Qp][kCandCap] u64 | cand_thr [G][Qp] u64 | cand_cnt [G][Qp] i32 | err flag (256 B) |
-//   progress counters (kProgressInts i32, zeroed by the launcher of the kernel that uses them)
+//   progress counters (kProgressInts i32) | gthr [Qp] u64   (both zeroed by the scoring-kernel launcher)
+// gthr[q] = best admission threshold any CTA has established for query q (atomicMax of a k-th key).  The k-th key
+// of ANY subset of the shard is a lower bound of the shard's k-th key, so every CTA may filter with it: the
+// admitted-candidate count (and with it the list compactions) drops from k*ln(N_cta/k) per CTA to ~that in total.
 struct TopkWorkspace {
   uint64_t* cand_keys;
   int* cand_cnt;
   uint64_t* cand_thr;
   int* err;
   int* progress;
+  unsigned long long* gthr;
   int workers;  // G
   int q_pad;    // Qp
 };
@@ -73,18 +77,20 @@ struct TopkWorkspace {
 
 inline size_t topk_workspace_bytes(int workers, int q_pad) {
   size_t n = size_t(workers) * q_pad;
-  return n * kCandCap * 8 + n * 8 + round_up(int(n * 4), 256) + 256 + kProgressInts * 4;
+  return n * kCandCap * 8 + n * 8 + round_up(int(n * 4), 256) + 256 + kProgressInts * 4 + size_t(q_pad) * 8;
 }
+// bytes of the zero-initialised tail (progress + gthr), starting at TopkWorkspace::progress
+inline size_t workspace_zero_bytes(int q_pad) { return size_t(kProgressInts) * 4 + size_t(q_pad) * 8; }
 inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
   TopkWorkspace w;
   size_t n = size_t(workers) * q_pad;
   char* p = static_cast<char*>(base);
   w.cand_keys = reinterpret_cast<uint64_t*>(p); p += n * kCandCap * 8;
   w.cand_thr = reinterpret_cast<uint64_t*>(p);  p += n * 8;
-  w.cand_cnt = reinterpret_cast<int*>(p);       p += n * 4;
-  p += round_up(int(n * 4), 256);
+  w.cand_cnt = reinterpret_cast<int*>(p);       p += round_up(int(n * 4), 256);
   w.err = reinterpret_cast<int*>(p);            p += 256;
-  w.progress = reinterpret_cast<int*>(p);
+  w.progress = reinterpret_cast<int*>(p);       p += kProgressInts * 4;
+  w.gthr = reinterpret_cast<unsigned long long*>(p);
   w.workers = workers;
   w.q_pad = q_pad;
   return w;

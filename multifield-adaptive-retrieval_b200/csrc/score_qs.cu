@@ -286,6 +286,10 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         }
         // ---- 64 docs scored under every field: + pre-mixed sparse term, threshold filter, push
         const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
+        if (q_valid) {                                 // adopt the best threshold any CTA found for this query
+          const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + qrow);
+          thr = gt > thr ? gt : thr;
+        }
         if (q_valid && doc0 < p.n_docs) {
           const int64_t left = p.n_docs - doc0;
           const int nd = left < kQsDocs ? int(left) : kQsDocs;
@@ -313,7 +317,11 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
           __syncwarp();
           const uint64_t kth = warp_compact_list(list_l, cnt_l, p.k, lane);
-          if (lane == l) { thr = kth; cnt = p.k; }
+          if (lane == l) {
+            thr = kth > thr ? kth : thr;
+            cnt = p.k;
+            atomicMax(p.ws.gthr + qrow, thr);
+          }
           __syncwarp();
         }
       }
@@ -384,8 +392,8 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
     MFAR_CUDA_OK(cudaFuncSetAttribute(score_qs_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
     attr_set = true;
   }
-  if (q_tiles / CG > 1)   // lockstep counters of the query groups (see the producer warp)
-    MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, sizeof(int) * kProgressInts, st));
+  // lockstep counters of the query groups (producer warp) + shared per-query thresholds (epilogue)
+  MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.q_pad), st));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(q_tiles, workers);
   cfg.blockDim = dim3(kQsThreads);

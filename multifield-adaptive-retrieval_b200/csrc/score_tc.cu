@@ -165,6 +165,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int u = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int t = g + i * gridDim.x;
+      {                                              // adopt the best threshold any CTA found for these queries
+        const int et0 = threadIdx.x - 64;
+        if (et0 < nq) {
+          const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + q0 + et0);
+          if (gt > s_thr[et0]) s_thr[et0] = gt;
+        }
+        epi_bar_sync();
+      }
 #pragma unroll
       for (int c = 0; c < QP; ++c) acc[c] = 0.f;
       for (int f = 0; f < p.n_dense; ++f, ++u) {
@@ -213,7 +221,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (cnt > kCandCap - kTileDocs) {
           uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
           const uint64_t kth = warp_compact_list(list, cnt, p.k, lane);
-          if (lane == 0) { s_thr[c] = kth; s_cnt[c] = p.k; }
+          if (lane == 0) {
+            if (kth > s_thr[c]) s_thr[c] = kth;
+            s_cnt[c] = p.k;
+            atomicMax(p.ws.gthr + q0 + c, s_thr[c]);
+          }
         }
       }
       epi_bar_sync();
@@ -280,6 +292,7 @@ static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
     MFAR_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
     attr_set = true;
   }
+  MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.q_pad), st));   // shared thresholds
   dim3 grid(workers, q_tiles);
   score_tc_kernel<QP><<<grid, kTcThreads, smem, st>>>(map_a, map_b, p);
   MFAR_CUDA_OK(cudaGetLastError());
