@@ -18,6 +18,9 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 
+FLAGS += [f"-D{d}" for d in os.environ.get("MFAR_DEFINES", "").split(",") if d]
+
+
 def _stale() -> bool:
     if not os.path.exists(OUT):
         return True

@@ -59,7 +59,8 @@ __host__ __device__ __forceinline__ uint32_t key_doc(uint64_t key) { return ~uin
 
 // Workspace carve-up shared by the scoring kernels and the merge.
 //   cand_keys [G][Qp][kCandCap] u64 | cand_thr [G][Qp] u64 | cand_cnt [G][Qp] i32 | err flag (256 B) |
-//   progress counters (kProgressInts i32) | gthr [Qp] u64   (both zeroed by the scoring-kernel launcher)
+//   progress counters (kProgressInts i32) | gthr [Qp] u64 | gpool [Qp] u64 | gpub [Qp] i32
+//   (the whole tail is zeroed by the scoring-kernel launcher)
 // gthr[q] = best admission threshold any CTA has established for query q (atomicMax of a k-th key).  The k-th key
 // of ANY subset of the shard is a lower bound of the shard's k-th key, so every CTA may filter with it: the
 // admitted-candidate count (and with it the list compactions) drops from k*ln(N_cta/k) per CTA to ~that in total.
@@ -70,6 +71,8 @@ struct TopkWorkspace {
   int* err;
   int* progress;
   unsigned long long* gthr;
+  unsigned long long* gpool;   // ~(min over CTAs of their rank-r key), r = ceil(k / #CTAs), see pooled_rank()
+  int* gpub;                   // how many CTAs have published into gpool[q]
   int workers;  // G
   int q_pad;    // Qp
 };
@@ -77,10 +80,10 @@ struct TopkWorkspace {
 
 inline size_t topk_workspace_bytes(int workers, int q_pad) {
   size_t n = size_t(workers) * q_pad;
-  return n * kCandCap * 8 + n * 8 + round_up(int(n * 4), 256) + 256 + kProgressInts * 4 + size_t(q_pad) * 8;
+  return n * kCandCap * 8 + n * 8 + round_up(int(n * 4), 256) + 256 + kProgressInts * 4 + size_t(q_pad) * 20;
 }
 // bytes of the zero-initialised tail (progress + gthr), starting at TopkWorkspace::progress
-inline size_t workspace_zero_bytes(int q_pad) { return size_t(kProgressInts) * 4 + size_t(q_pad) * 8; }
+inline size_t workspace_zero_bytes(int q_pad) { return size_t(kProgressInts) * 4 + size_t(q_pad) * 20; }
 inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
   TopkWorkspace w;
   size_t n = size_t(workers) * q_pad;
@@ -90,7 +93,9 @@ inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
   w.cand_cnt = reinterpret_cast<int*>(p);       p += round_up(int(n * 4), 256);
   w.err = reinterpret_cast<int*>(p);            p += 256;
   w.progress = reinterpret_cast<int*>(p);       p += kProgressInts * 4;
-  w.gthr = reinterpret_cast<unsigned long long*>(p);
+  w.gthr = reinterpret_cast<unsigned long long*>(p);   p += size_t(q_pad) * 8;
+  w.gpool = reinterpret_cast<unsigned long long*>(p);  p += size_t(q_pad) * 8;
+  w.gpub = reinterpret_cast<int*>(p);
   w.workers = workers;
   w.q_pad = q_pad;
   return w;
@@ -131,6 +136,13 @@ __device__ __forceinline__ void warp_sort256_desc(uint64_t (&v)[8], int lane) {
     }
   }
 }
+
+// Pooled threshold.  If every one of the G CTAs scanning a query's shard holds at least r = ceil(k/G) keys >= x_g,
+// then min_g(x_g) has at least G*r >= k keys above it shard-wide: a valid admission threshold that is far tighter
+// than any single CTA's own k-th key early on (after the first compaction round it is roughly the k-th best of ALL
+// docs scanned so far by all CTAs, not of one CTA's slice), which removes most later compaction rounds.
+// Each CTA publishes the rank-r key of its sorted list once (first compaction); gpool holds ~min via atomicMax(~key).
+__host__ __device__ inline int pooled_rank(int k, int G) { return (k + G - 1) / G; }
 
 // One warp compacts the candidate list of one (worker, query): keep the best k keys (sorted
 // descending), return the k-th key (new admission threshold).  `list` points at kCandCap slots

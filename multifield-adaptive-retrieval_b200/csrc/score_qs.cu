@@ -96,6 +96,9 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
+#ifdef MFAR_QS_TIMING
+  const long long t_kernel0 = clock64();
+#endif
   const int g = blockIdx.y;                        // worker: walks tiles g, g+G, ...
   const int G = gridDim.y;
   const int q0 = blockIdx.x * kQsQ;                // first query of this CTA
@@ -155,6 +158,11 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
 
   const int my_tiles = (p.n_tiles > g) ? (p.n_tiles - g + G - 1) / G : 0;
   const int units = my_tiles * 2 * p.n_dense;      // (tile, half, field)
+#ifdef MFAR_QS_TIMING
+  const long long t_setup_done = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    printf("[qs timing] setup (barriers, TMEM alloc, queries -> TMEM) %lld cycles\n", t_setup_done - t_kernel0);
+#endif
 
   if (warp == 0) {
     // ===================================================================== TMA producer (every CTA)
@@ -220,14 +228,22 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
       const int buf = (warp == 1) ? 0 : 1;
       const uint32_t issue = elect_one() ? 1u : 0u;
       const uint32_t d_tmem = tmem_base + uint32_t(kQsDCol + buf * kQsDocs);
+#ifdef MFAR_QS_TIMING
+      long long t_tempty = 0, t_full = 0, t_issue = 0, t_prev = clock64();
+#define QS_TICK(acc) { const long long _n = clock64(); acc += _n - t_prev; t_prev = _n; }
+#else
+#define QS_TICK(acc)
+#endif
       for (int u = buf; u < units; u += 2) {
         mbar_wait(&tempty_bar[buf], ((u >> 1) & 1) ^ 1, err, 13);
+        QS_TICK(t_tempty)
         tc_fence_after();
         for (int s = 0; s < stages_per_unit; ++s) {
           const int ring = u * stages_per_unit + s;   // position in the producer's stage sequence
           const int stage = ring % p.stages;
           const uint32_t phase = uint32_t(ring / p.stages) & 1u;
           mbar_wait(&full_bar[stage], phase, err, 14);
+          QS_TICK(t_full)
           tc_fence_after();
           const uint32_t stage_addr = smem_u32(smem_b + size_t(stage) * kStageBytes);
           const uint64_t desc0 = make_sw128_desc(stage_addr);
@@ -244,7 +260,14 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         }
         if (elect_one()) { if (CG == 2) tc_commit_cg2(&tfull_bar[buf], 0x3); else tc_commit(&tfull_bar[buf]); }
         __syncwarp();
+        QS_TICK(t_issue)
       }
+#ifdef MFAR_QS_TIMING
+      if (lane == 0 && blockIdx.y == 0 && blockIdx.x == 0)
+        printf("[qs timing] issuer %d: units %d  cycles/unit: wait_tempty %.0f wait_full %.0f issue %.0f\n", buf,
+               (units + 1 - buf) / 2, double(t_tempty) / ((units + 1 - buf) / 2), double(t_full) / ((units + 1 - buf) / 2),
+               double(t_issue) / ((units + 1 - buf) / 2));
+#endif
     }
   } else {
     // ===================================================================== epilogue: thread = query
@@ -256,8 +279,16 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     const float* my_base = p.base ? p.base + int64_t(q_valid ? qrow : 0) * p.base_ld : nullptr;
     uint64_t thr = 0ull;
     int cnt = 0;
+    bool published = false, pool_adopted = false;
     float acc[kQsDocs];
     int u = 0;
+#ifdef MFAR_QS_TIMING
+    long long e_wait = 0, e_drain = 0, e_push = 0, e_compact = 0, e_prev = clock64();
+    int n_compact = 0;
+#define QS_ETICK(acc_) { const long long _n = clock64(); acc_ += _n - e_prev; e_prev = _n; }
+#else
+#define QS_ETICK(acc_)
+#endif
     for (int i = 0; i < my_tiles; ++i) {
       const int t = g + i * G;
       for (int h = 0; h < 2; ++h) {
@@ -266,29 +297,36 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         for (int f = 0; f < p.n_dense; ++f, ++u) {
           const int buf = u & 1;
           mbar_wait(&tfull_bar[buf], (u >> 1) & 1, err, 15);
+          QS_ETICK(e_wait)
           tc_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(kQsDCol + buf * kQsDocs);
           const float wf = w_s[f * kQsQ + qloc];
+          // drain the whole accumulator into registers and hand the TMEM buffer back BEFORE the FMAs: the
+          // release -> next MMA chain (cross-CTA in pair mode) is what bounds the unit rate, not the arithmetic
+          uint32_t v[kQsDocs];
 #pragma unroll
-          for (int c0 = 0; c0 < kQsDocs; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-            tmem_ld16(taddr + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) acc[c0 + c] = fmaf(wf, __uint_as_float(v[c]), acc[c0 + c]);
-          }
+          for (int c0 = 0; c0 < kQsDocs; c0 += 16)
+            tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
+          tmem_ld_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {                           // one arrival per epilogue warp frees the accumulator buffer
             if (CG == 2) mbar_arrive_cluster_rank0(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
           }
+#pragma unroll
+          for (int c = 0; c < kQsDocs; ++c) acc[c] = fmaf(wf, __uint_as_float(v[c]), acc[c]);
+          QS_ETICK(e_drain)
         }
         // ---- 64 docs scored under every field: + pre-mixed sparse term, threshold filter, push
         const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
         if (q_valid) {                                 // adopt the best threshold any CTA found for this query
           const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + qrow);
           thr = gt > thr ? gt : thr;
+          if (!pool_adopted && ld_relaxed_s32(p.ws.gpub + qrow) == G) {   // every CTA of this query has published
+            const unsigned long long pt = ~ld_relaxed_u64(p.ws.gpool + qrow);
+            thr = pt > thr ? pt : thr;
+            pool_adopted = true;
+          }
         }
         if (q_valid && doc0 < p.n_docs) {
           const int64_t left = p.n_docs - doc0;
@@ -308,8 +346,12 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
             if (c < nd && key > thr) { __stcg(my_list + cnt, key); ++cnt; }
           }
         }
+        QS_ETICK(e_push)
         // ---- lists that could overflow on the next unit are compacted by the whole warp, one at a time
         unsigned need = __ballot_sync(0xffffffffu, cnt > kCandCap - kQsDocs);
+#ifdef MFAR_QS_TIMING
+        n_compact += __popc(need);
+#endif
         while (need) {
           const int l = __ffs(need) - 1;
           need &= need - 1;
@@ -317,15 +359,29 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
           __syncwarp();
           const uint64_t kth = warp_compact_list(list_l, cnt_l, p.k, lane);
+          __syncwarp();
           if (lane == l) {
             thr = kth > thr ? kth : thr;
             cnt = p.k;
             atomicMax(p.ws.gthr + qrow, thr);
+            if (!published) {                          // first compaction of this list: publish its rank-r key
+              published = true;
+              const unsigned long long key_r = __ldcg(list_l + pooled_rank(p.k, G) - 1);
+              atomicMax(p.ws.gpool + qrow, ~key_r);
+              __threadfence();
+              atomicAdd(p.ws.gpub + qrow, 1);
+            }
           }
           __syncwarp();
         }
+        QS_ETICK(e_compact)
       }
     }
+#ifdef MFAR_QS_TIMING
+    if (lane == 0 && blockIdx.y == 0 && blockIdx.x == 0)
+      printf("[qs timing] epilogue warp %d: units %d kcycles: wait %lld drain %lld push %lld compact %lld (lists compacted %d)\n",
+             warp, units, e_wait / 1000, e_drain / 1000, e_push / 1000, e_compact / 1000, n_compact);
+#endif
     if (q_valid) {
       p.ws.cand_cnt[int64_t(g) * p.ws.q_pad + qrow] = cnt;
       p.ws.cand_thr[int64_t(g) * p.ws.q_pad + qrow] = thr;

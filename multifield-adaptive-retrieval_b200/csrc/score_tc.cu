@@ -60,7 +60,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   float* w_s = reinterpret_cast<float*>(smem_b + size_t(p.k_chunks) * b_chunk_bytes);     // [n_dense][QP]
   unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(w_s + size_t(p.n_dense) * QP);
   int* s_cnt = reinterpret_cast<int*>(s_thr + QP);
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_cnt + QP) + 7) & ~uintptr_t(7));
+  int* s_flags = s_cnt + QP;                       // bit 0: published to gpool, bit 1: pooled threshold adopted
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_flags + QP) + 7) & ~uintptr_t(7));
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + p.stages;           // [stages]
   uint64_t* tfull_bar = bars + 2 * p.stages;       // [2]
@@ -81,7 +82,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int f = i / QP, c = i % QP;
     w_s[i] = (c < nq) ? p.w[int64_t(q0 + c) * p.w_ld + f] : 0.f;
   }
-  if (threadIdx.x < QP) { s_thr[threadIdx.x] = 0ull; s_cnt[threadIdx.x] = 0; }
+  if (threadIdx.x < QP) { s_thr[threadIdx.x] = 0ull; s_cnt[threadIdx.x] = 0; s_flags[threadIdx.x] = 0; }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -170,6 +171,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (et0 < nq) {
           const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + q0 + et0);
           if (gt > s_thr[et0]) s_thr[et0] = gt;
+          if (!(s_flags[et0] & 2) && ld_relaxed_s32(p.ws.gpub + q0 + et0) == int(gridDim.x)) {
+            const unsigned long long pt = ~ld_relaxed_u64(p.ws.gpool + q0 + et0);   // pooled threshold, common.cuh
+            if (pt > s_thr[et0]) s_thr[et0] = pt;
+            s_flags[et0] |= 2;
+          }
         }
         epi_bar_sync();
       }
@@ -221,10 +227,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (cnt > kCandCap - kTileDocs) {
           uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
           const uint64_t kth = warp_compact_list(list, cnt, p.k, lane);
+          __syncwarp();
           if (lane == 0) {
             if (kth > s_thr[c]) s_thr[c] = kth;
             s_cnt[c] = p.k;
             atomicMax(p.ws.gthr + q0 + c, s_thr[c]);
+            if (!(s_flags[c] & 1)) {                   // first compaction of this list: publish its rank-r key
+              s_flags[c] |= 1;
+              const unsigned long long key_r = __ldcg(list + pooled_rank(p.k, int(gridDim.x)) - 1);
+              atomicMax(p.ws.gpool + q0 + c, ~key_r);
+              __threadfence();
+              atomicAdd(p.ws.gpub + q0 + c, 1);
+            }
           }
         }
       }
@@ -263,7 +277,7 @@ void score_tc_geometry(int Q, int n_tiles, int* q_pad, int* q_tiles, int* worker
 
 static size_t tc_smem_bytes(int qp, int n_dense, int k_chunks, int stages) {
   return 1024 + size_t(stages) * kABytes + size_t(k_chunks) * qp * kChunkK * 2 + size_t(n_dense) * qp * 4 +
-         size_t(qp) * 12 + 8 + (2 * stages + 5) * 8 + 16;
+         size_t(qp) * 16 + 8 + (2 * stages + 5) * 8 + 16;
 }
 
 template <int QP>
