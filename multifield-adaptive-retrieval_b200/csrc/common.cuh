@@ -168,4 +168,57 @@ __device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, int count,
   return __shfl_sync(0xffffffffu, kth, (k - 1) >> 3);
 }
 
+// Cheaper compaction for every round after the first: instead of sorting, binary-search the 32-bit score word for
+// the largest T with count(score >= T) >= k (a warp-wide count per probe: 8 compares + one REDUX), stop as soon as
+// k <= count <= k + kSelectSlack, and keep exactly those keys (ballot-compacted, unsorted).  ~1/5 of the sort's
+// instructions.  Returns the admission threshold "(T << 32) - 1" (key > thr  <=>  score word >= T) and the new
+// count through *new_count.  Falls back to the exact sort when score ties keep too many keys.
+constexpr int kSelectSlack = 24;
+
+__device__ __forceinline__ uint64_t warp_select_list(uint64_t* list, int count, int k, int max_keep, int lane,
+                                                     int* new_count) {
+  // max_keep: the caller's list may hold at most this many keys after compaction (its overflow trigger level)
+  const int slack = min(kSelectSlack, max_keep - k);
+  uint64_t v[8];
+  uint32_t hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int e = lane * 8 + j;
+    v[j] = (e < count) ? __ldcg(list + e) : 0ull;
+    hi[j] = uint32_t(v[j] >> 32);                       // 0 for empty slots: below every real score word
+  }
+  uint32_t mx = 0u, mn = 0xFFFFFFFFu;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mx = max(mx, hi[j]);
+    if (v[j] != 0ull) mn = min(mn, hi[j]);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  uint32_t lo = mn, up = mx;                            // invariant: count(>= lo) >= k;  answer in [lo, up]
+  int c_lo = count;
+  while (lo < up && c_lo > k + slack) {
+    const uint32_t mid = lo + ((up - lo + 1u) >> 1);    // lo < mid <= up
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c += (hi[j] >= mid) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) { lo = mid; c_lo = c; } else { up = mid - 1u; }
+  }
+  if (c_lo > k + slack) {                               // a big tie group straddles rank k (or no slack): exact path
+    *new_count = k;
+    return warp_compact_list(list, count, k, lane);
+  }
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool keep = hi[j] >= lo && v[j] != 0ull;
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (keep) __stcg(list + base + __popc(b & ((1u << lane) - 1u)), v[j]);
+    base += __popc(b);
+  }
+  *new_count = base;
+  return (uint64_t(lo) << 32) - 1ull;
+}
+
 }  // namespace mfar

@@ -358,11 +358,14 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
           uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
           __syncwarp();
-          const uint64_t kth = warp_compact_list(list_l, cnt_l, p.k, lane);
+          const bool first_l = __shfl_sync(0xffffffffu, int(published), l) == 0;
+          int cnt_new = p.k;                           // first round: exact sort (its rank-r key is published);
+          const uint64_t kth = first_l ? warp_compact_list(list_l, cnt_l, p.k, lane)   // later rounds: cheap select
+                                       : warp_select_list(list_l, cnt_l, p.k, kCandCap - kQsDocs, lane, &cnt_new);
           __syncwarp();
           if (lane == l) {
             thr = kth > thr ? kth : thr;
-            cnt = p.k;
+            cnt = cnt_new;
             atomicMax(p.ws.gthr + qrow, thr);
             if (!published) {                          // first compaction of this list: publish its rank-r key
               published = true;

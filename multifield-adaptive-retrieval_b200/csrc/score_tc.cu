@@ -226,11 +226,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int cnt = s_cnt[c];
         if (cnt > kCandCap - kTileDocs) {
           uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
-          const uint64_t kth = warp_compact_list(list, cnt, p.k, lane);
+          int cnt_new = p.k;                           // first round: exact sort (its rank-r key is published);
+          const uint64_t kth = !(s_flags[c] & 1) ? warp_compact_list(list, cnt, p.k, lane)   // later: cheap select
+                                                 : warp_select_list(list, cnt, p.k, kCandCap - kTileDocs, lane, &cnt_new);
           __syncwarp();
           if (lane == 0) {
             if (kth > s_thr[c]) s_thr[c] = kth;
-            s_cnt[c] = p.k;
+            s_cnt[c] = cnt_new;
             atomicMax(p.ws.gthr + q0 + c, s_thr[c]);
             if (!(s_flags[c] & 1)) {                   // first compaction of this list: publish its rank-r key
               s_flags[c] |= 1;
