@@ -340,10 +340,15 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
             }
           }
           const uint32_t id0 = uint32_t(p.doc_id_base + doc0);
+          // one float compare per doc rejects almost everything; the exact (score, id) key is only built for docs
+          // whose score reaches the threshold's score (thr == 0: nothing established yet, admit all)
+          const float thr_f = thr ? key_score(thr) : -INFINITY;
 #pragma unroll
           for (int c = 0; c < kQsDocs; ++c) {
-            const uint64_t key = make_key(acc[c], id0 + c);
-            if (c < nd && key > thr) { __stcg(my_list + cnt, key); ++cnt; }
+            if (c < nd && acc[c] >= thr_f) {
+              const uint64_t key = make_key(acc[c], id0 + c);
+              if (key > thr) { __stcg(my_list + cnt, key); ++cnt; }
+            }
           }
         }
         QS_ETICK(e_push)
