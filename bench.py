@@ -252,7 +252,18 @@ def main():
     with torch.no_grad():
         layer.weight.copy_(synth.make_mixture(DIM, F, args.seed + 1))
     retr = MultiFieldRetriever(pc, layer.to(device), n_sparse=n_sparse, top_k=TOPK, doc_id_base=lo, impl=args.kernel)
-    sharded = ShardedRetriever(retr)
+    exchange, exchange_kind = None, "none (1 GPU)"
+    if world > 1:
+        from mfar_b200.dist import PeerExchange
+        if os.environ.get("MFAR_EXCHANGE", "p2p") == "p2p":
+            try:
+                exchange = PeerExchange(q_cap=max(1024, Q), k_cap=128, device=device)
+                exchange_kind = "fused NVLink peer-memory exchange+merge kernel (mfar_topk_exchange_merge)"
+            except Exception as e:  # noqa: BLE001  (symmetric memory unavailable: NCCL all-gather + merge kernel)
+                exchange_kind = f"nccl all_gather + merge kernel (peer exchange unavailable: {type(e).__name__}: {e})"[:300]
+        else:
+            exchange_kind = "nccl all_gather + merge kernel"
+    sharded = ShardedRetriever(retr, exchange=exchange)
     setup_s = time.perf_counter() - t_setup
 
     def make_batches(q_count, n_pool=4):
@@ -421,7 +432,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "path": "mfar_search_host (C ABI, pinned host buffers)" if world == 1 else
                             "pinned host -> device copies + sharded search + D2H of the merged top-k"},
-            "gpu_launches": launches, "clocks": clocks, "other_batches": extra, "setup_s": setup_s,
+            "gpu_launches": launches, "exchange": exchange_kind, "clocks": clocks, "other_batches": extra, "setup_s": setup_s,
             "kernel_impl": args.kernel,
         }
         print(json.dumps(line))

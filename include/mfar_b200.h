@@ -140,6 +140,19 @@ MFAR_API int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fiel
 MFAR_API int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_t* out_keys,
                     float* out_scores, int64_t* out_ids, void* stream);
 
+/* Cross-GPU exchange + merge in one kernel over NVLink peer memory (no NCCL call on the data path): every rank pushes
+ * its [Q,k_in] keys into all peers' exchange buffers, waits for theirs, merges.  Replaces, together with
+ * mfar_score_topk, the {rank}.qres file exchange of mfar/modeling/contrastive.py:566-581,616-631.
+ *   peer_buffers_host: HOST array of `world` device addresses; entry r = rank r's exchange buffer as mapped into
+ *     THIS process (CUDA VMM / IPC; torch.distributed._symmetric_memory provides them), each of
+ *     mfar_exchange_buffer_bytes(world, q_cap, k_cap) bytes, zero-filled once before the first call;
+ *   epoch: 1, 2, 3, ... - must increase by one per call, identically on every rank;
+ *   every rank must call with the same Q, k_in, k.  world <= 8, world * k_in <= 1024. */
+MFAR_API size_t mfar_exchange_buffer_bytes(int world, int q_cap, int k_cap);
+MFAR_API int mfar_topk_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
+                             const uint64_t* peer_buffers_host, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
+                             float* out_scores, int64_t* out_ids, void* stream);
+
 /* Reference quirk, mfar/data/index.py:192-193: the running top-k starts as k entries of
  * (score 0.0, row 0).  Applies that to a finished [Q,k] result in place: entries scoring
  * below 0.0 are replaced by (0.0, 0) and the list re-sorted. */

@@ -268,6 +268,81 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Cross-GPU exchange + merge in ONE kernel over NVLink peer memory (replaces ncclAllGather + merge).
+// Every rank owns a buffer [flags: 2][world][q_cap] i32 | [keys: 2][world][q_cap][k_cap] u64 that all peers have
+// mapped (CUDA VMM / torch symmetric memory).  One CTA per query:
+//   1. PUSH   the rank's local top-k keys of this query into slot [parity][rank][q] of EVERY rank's buffer
+//             (st.global on peer-mapped addresses -> NVLink), then, after a system-scope fence, the flag = epoch;
+//   2. WAIT   until the flags of all ranks for this query show `epoch` in the LOCAL buffer (ld.acquire.sys);
+//   3. MERGE  the world * k_in keys (now local) with the block bitonic sort and emit the global top-k.
+// Buffers alternate by epoch parity: a peer can only be one call ahead (it needs this rank's next push to finish
+// its next call), so two slots are enough.  CTAs push before they wait and are scheduled in query order on every
+// rank, so the resident CTAs of all ranks always contain the lowest unfinished query: no deadlock.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct PeerBufs { unsigned long long base[kMaxPeers]; };
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int k_in, PeerBufs peers, int rank, int world, int q_cap,
+                      int k_cap, int epoch, int k, uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
+                      int64_t* __restrict__ out_ids, int* __restrict__ err) {
+  __shared__ uint64_t buf[kMergeBuf];
+  const int q = blockIdx.x, t = threadIdx.x;
+  const int parity = epoch & 1;
+  const size_t flag_bytes = size_t(2) * world * q_cap * sizeof(int);
+  const size_t slot = (size_t(parity) * world + rank) * q_cap + q;            // [parity][rank][q]
+  // 1. push
+  for (int i = t; i < world * k_in; i += kMergeThreads) {
+    const int r = i / k_in, j = i % k_in;
+    uint64_t* dst = reinterpret_cast<uint64_t*>(peers.base[r] + flag_bytes) + slot * k_cap + j;
+    *dst = __ldg(local_keys + int64_t(q) * k_in + j);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < world) st_release_sys(reinterpret_cast<int*>(peers.base[t]) + slot, epoch);
+  // 2. wait (bounded: a peer that never arrives becomes an error, not a hang)
+  if (t < world) {
+    const int* f = reinterpret_cast<const int*>(peers.base[rank]) + (size_t(parity) * world + t) * q_cap + q;
+    const unsigned long long t0 = clock64();
+    while (ld_acquire_sys(f) != epoch) {
+      if (clock64() - t0 > 20000000000ull) {                                  // ~10 s
+        atomicExch(err, 31);
+        __threadfence_system();
+        asm volatile("trap;");
+      }
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  // 3. merge (all data is in this rank's own buffer now)
+  const uint64_t* mine = reinterpret_cast<const uint64_t*>(peers.base[rank] + flag_bytes);
+  for (int i = t; i < kMergeBuf; i += kMergeThreads) {
+    uint64_t key = 0ull;
+    if (i < world * k_in) {
+      const int r = i / k_in, j = i % k_in;
+      key = __ldcg(mine + ((size_t(parity) * world + r) * q_cap + q) * k_cap + j);
+    }
+    buf[i] = key;
+  }
+  block_sort1024_desc(buf);
+  for (int j = t; j < k; j += kMergeThreads) {
+    const uint64_t key = buf[j];
+    if (out_keys) out_keys[int64_t(q) * k + j] = key;
+    if (out_scores) out_scores[int64_t(q) * k + j] = key ? key_score(key) : -INFINITY;
+    if (out_ids) out_ids[int64_t(q) * k + j] = key ? int64_t(key_doc(key)) : int64_t(-1);
+  }
+}
+
 // index.py:192-193 quirk: running top-k starts as (0.0, row 0) entries.
 __global__ void zero_init_kernel(float* scores, int64_t* ids, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,6 +429,21 @@ int launch_sparse_premix(const void* sparse, int sparse_dtype, int64_t sparse_ld
 int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
                  int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   merge_kernel<<<Q, kMergeThreads, 0, st>>>(keys, counts, thr, L, q_stride, slots, k, out_keys, out_scores, out_ids);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
+                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
+                          float* out_scores, int64_t* out_ids, cudaStream_t st) {
+  if (world < 1 || world > kMaxPeers || world * k_in > kMergeBuf || Q > q_cap || k_in > k_cap) return MFAR_ERR_SHAPE;
+  PeerBufs pb{};
+  for (int r = 0; r < world; ++r) pb.base[r] = peer_bases[r];
+  // the error word lives at the very end of this rank's buffer
+  int* err = reinterpret_cast<int*>(pb.base[rank] + size_t(2) * world * q_cap * sizeof(int) +
+                                    size_t(2) * world * q_cap * k_cap * sizeof(uint64_t));
+  exchange_merge_kernel<<<Q, kMergeThreads, 0, st>>>(local_keys, k_in, pb, rank, world, q_cap, k_cap, epoch, k, out_keys,
+                                                     out_scores, out_ids, err);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }

@@ -220,6 +220,25 @@ int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_
                       static_cast<cudaStream_t>(stream));
 }
 
+size_t mfar_exchange_buffer_bytes(int world, int q_cap, int k_cap) {
+  if (world < 1 || world > 8 || q_cap <= 0 || k_cap <= 0) return 0;
+  return align_up(size_t(2) * world * q_cap * sizeof(int) + size_t(2) * world * q_cap * k_cap * sizeof(uint64_t) + 16, 256);
+}
+
+int mfar_topk_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
+                             const uint64_t* peer_buffers_host, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
+                             float* out_scores, int64_t* out_ids, void* stream) {
+  if (!local_keys || !peer_buffers_host || Q <= 0 || k_in <= 0 || rank < 0 || rank >= world || epoch <= 0)
+    return MFAR_ERR_ARG;
+  if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
+  for (int r = 0; r < world; ++r)
+    if (!peer_buffers_host[r] || peer_buffers_host[r] % 16 != 0) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  return launch_exchange_merge(local_keys, Q, k_in, k, rank, world,
+                               reinterpret_cast<const unsigned long long*>(peer_buffers_host), q_cap, k_cap, epoch,
+                               out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+}
+
 int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* stream) {
   if (!scores || !ids || Q <= 0 || k <= 0) return MFAR_ERR_ARG;
   if (int rc = check_arch()) return rc;

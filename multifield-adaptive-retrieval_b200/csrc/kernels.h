@@ -22,6 +22,9 @@ int launch_sparse_premix(const void* sparse, int sparse_dtype, int64_t sparse_ld
 int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
                  int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
 int launch_zero_init(float* scores, int64_t* ids, int n, cudaStream_t st);
+int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
+                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
+                          float* out_scores, int64_t* out_ids, cudaStream_t st);
 
 // Arguments common to both scoring kernels (all device pointers).
 struct ScoreArgs {

@@ -61,13 +61,62 @@ def merge_keys(all_keys: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tens
     return scores, ids
 
 
+class PeerExchange:
+    """Per-shard [Q,k] key lists exchanged and merged by ONE kernel over NVLink peer memory
+    (``mfar_topk_exchange_merge``): every rank stores its keys straight into all peers' exchange buffers, spins on
+    per-query flags, merges locally.  No NCCL call on the data path; ``torch.distributed._symmetric_memory`` is only
+    the plumbing that maps the peers' buffers into this process (CUDA VMM handles exchanged at rendezvous)."""
+
+    def __init__(self, q_cap: int, k_cap: int = 128, group=None, device=None, peer_buffers=None, rank=None, world=None):
+        self.q_cap, self.k_cap = int(q_cap), int(k_cap)
+        self.epoch = 0
+        if peer_buffers is not None:                      # explicit buffers (tests: "virtual ranks" on one device)
+            self.rank, self.world = int(rank), int(world)
+            self._bufs = peer_buffers
+            self.ptrs = [int(b.data_ptr()) for b in peer_buffers]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = group or dist.group.WORLD
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+            n = nv.lib().mfar_exchange_buffer_bytes(self.world, self.q_cap, self.k_cap)
+            buf = symm_mem.empty(n, dtype=torch.uint8, device=device or torch.device("cuda", torch.cuda.current_device()))
+            buf.zero_()
+            self._hdl = symm_mem.rendezvous(buf, group.group_name if hasattr(group, "group_name") else group)
+            self._bufs = [buf]
+            self.ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            torch.cuda.synchronize()
+            dist.barrier(group)                           # every rank's flags are zero before anyone pushes
+        import ctypes
+        self._ptr_arr = (ctypes.c_uint64 * self.world)(*self.ptrs)
+
+    @staticmethod
+    def buffer_bytes(world: int, q_cap: int, k_cap: int = 128) -> int:
+        return nv.lib().mfar_exchange_buffer_bytes(world, q_cap, k_cap)
+
+    def merge(self, keys: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """keys: int64 view of this rank's packed keys [Q,k_in] (device) -> global (scores [Q,k], ids [Q,k])."""
+        import ctypes
+        nv.require_device(keys, "keys")
+        Q, k_in = keys.shape
+        if Q > self.q_cap or k_in > self.k_cap:
+            raise ValueError(f"exchange buffers sized for [{self.q_cap},{self.k_cap}], got [{Q},{k_in}]")
+        self.epoch += 1
+        scores = torch.empty((Q, k), dtype=torch.float32, device=keys.device)
+        ids = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
+        nv.check(nv.lib().mfar_topk_exchange_merge(nv.ptr(keys.contiguous()), Q, k_in, k, self.rank, self.world,
+                                                   ctypes.addressof(self._ptr_arr), self.q_cap, self.k_cap, self.epoch,
+                                                   0, nv.ptr(scores), nv.ptr(ids), nv.stream()), "topk_exchange_merge")
+        return scores, ids
+
+
 class ShardedRetriever:
     """One process per GPU; wraps the rank-local ``MultiFieldRetriever`` (built over this rank's doc
     range with ``doc_id_base = shard_range(...)[0]``)."""
 
-    def __init__(self, local, group=None):
+    def __init__(self, local, group=None, exchange: Optional[PeerExchange] = None):
         self.local = local
         self.group = group
+        self.exchange = exchange          # None: NCCL/gloo all-gather + merge kernel; else the fused NVLink kernel
 
     @torch.no_grad()
     def search(self, q_vecs, q_emb=None, sparse_local=None, top_k: Optional[int] = None):
@@ -78,4 +127,6 @@ class ShardedRetriever:
             keys = torch.nn.functional.pad(keys, (0, k - k_local))
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return merge_keys(keys.unsqueeze(0), k)
+        if self.exchange is not None:
+            return self.exchange.merge(keys, k)
         return merge_keys(all_gather_keys(keys, self.group), k)

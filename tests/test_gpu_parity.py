@@ -321,6 +321,32 @@ def test_virtual_shards_merge_equals_single_shard(impl):
         assert torch.equal(i, i0) and torch.equal(s, s0), R
 
 
+def test_peer_exchange_merge_virtual_ranks():
+    """The fused NVLink exchange+merge kernel with R "virtual ranks" on one device: R exchange buffers, R concurrent
+    streams, each rank pushing into all buffers and spinning on its own flags.  Three epochs (both parities and a
+    buffer reuse).  Must equal a single merge of the concatenated lists."""
+    from mfar_b200.dist import PeerExchange, encode_keys, merge_keys
+    R, Q, k = 4, 9, 100
+    n = PeerExchange.buffer_bytes(R, 16, 128)
+    bufs = [torch.zeros(n, dtype=torch.uint8, device=DEV) for _ in range(R)]
+    ex = [PeerExchange(16, 128, peer_buffers=bufs, rank=r, world=R) for r in range(R)]
+    streams = [torch.cuda.Stream() for _ in range(R)]
+    g = np.random.RandomState(5)
+    for epoch in range(3):
+        scores = g.standard_normal((R, Q, k)).astype(np.float32) * 10
+        ids = np.stack([g.permutation(100000)[: Q * k].reshape(Q, k) + 100000 * r for r in range(R)])
+        keys = torch.from_numpy(encode_keys(scores, ids).view(np.int64)).to(DEV)         # [R,Q,k]
+        want_s, want_i = merge_keys(keys, k)
+        torch.cuda.synchronize()
+        outs = []
+        for r in range(R):
+            with torch.cuda.stream(streams[r]):
+                outs.append(ex[r].merge(keys[r], k))
+        torch.cuda.synchronize()
+        for s_r, i_r in outs:
+            assert torch.equal(s_r, want_s) and torch.equal(i_r, want_i)
+
+
 def test_topk_edge_cases():
     fields, q, _, W = synth(51, 300, 64, 2, 0, 2, False)
     r = build(fields, W, False, 0, 100)
