@@ -270,7 +270,7 @@ def main():
         pool = []
         for i in range(n_pool):
             qv = synth.make_queries(q_count, DIM, mu, args.seed + 100 + i, device)
-            sp = synth.make_sparse(q_count, n_sparse, hi - lo, args.seed + 200 + i, device)
+            sp = synth.make_sparse(q_count, n_sparse, hi - lo, args.seed + 200 + i, device, pitch=8)
             pool.append((qv, qv.float(), sp))
         return pool
 
@@ -341,7 +341,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # e2e: N=1 goes through mfar_search_host; N>1 adds the (device) key exchange + merge per step
-    pool_host = [(qv.cpu().pin_memory(), qe.cpu().pin_memory(), None if sp is None else sp.cpu().pin_memory())
+    pool_host = [(qv.cpu().pin_memory(), qe.cpu().pin_memory(),
+                  None if sp is None else sp[:, :, :hi - lo].contiguous().cpu().pin_memory())   # host call: pitch = N
                  for qv, qe, sp in pool_dev]
     if world == 1:
         ms_e2e = run_e2e(pool_host, args.steps, args.warmup)

@@ -133,6 +133,19 @@ MFAR_API int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fiel
                     float* out_scores, int64_t* out_ids, void* workspace, size_t workspace_bytes, int impl,
                     void* stream);
 
+/* Same pass with the sparse scores in the reference's precomputed-BM25 file layout instead of a dense tensor
+ * (mfar/commands/precompute_bm25s_scores.py:21-30, read back by read_sparse_scores, mfar/modeling/util.py:151-173,
+ * looked up by BM25sSparseIndex.score_batch_with_cache, mfar/data/index.py:120-125 - missing pairs score 0):
+ *   coo_keys   int32 [nnz,2]: (query row in this batch, GLOBAL doc row); rows of other shards / batches are skipped
+ *   coo_vals   [nnz] f16 (the file dtype) or f32
+ *   field_offsets_host  HOST int64 [n_sparse+1]: entries [off[j], off[j+1]) belong to sparse field j; off[0] = 0
+ * Duplicate (query, field, doc) entries add up. */
+MFAR_API int mfar_score_topk_coo(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
+                        int dim, const void* q_vecs, int Q, const float* w, const int32_t* coo_keys,
+                        const void* coo_vals, int coo_dtype, const int64_t* field_offsets_host, int n_sparse,
+                        int64_t doc_id_base, int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                        void* workspace, size_t workspace_bytes, int impl, void* stream);
+
 /* Merge L sorted-or-unsorted key lists per query into the global top-k.  Used for (a) the
  * per-CTA partial lists inside mfar_score_topk and (b) the per-shard lists after the NCCL
  * all-gather (replaces the {rank}.qres file merge of mfar/modeling/contrastive.py:616-631).

@@ -149,6 +149,59 @@ __global__ void sparse_premix_kernel(const ST* __restrict__ sparse, int64_t spar
   base[int64_t(q) * base_ld + n] = acc;
 }
 
+// COO variant (the reference's precomputed-BM25 file format, precompute_bm25s_scores.py:21-30: int32 (query, doc)
+// pairs + one value per pair, one segment per sparse field): base[q, doc - doc_id_base] += w[q, F_d + j] * val.
+// base is zeroed by the launcher; atomics only collide between different fields of the same (query, doc).
+struct CooFieldOffsets { long long off[MFAR_MAX_FIELDS + 1]; };
+
+template <typename VT>
+__global__ void sparse_premix_coo_kernel(const int2* __restrict__ keys, const VT* __restrict__ vals, CooFieldOffsets fo,
+                                         int n_sparse, const float* __restrict__ w, int w_ld, int w_off, int Q,
+                                         int64_t doc_id_base, int64_t n_docs, float* __restrict__ base,
+                                         int64_t base_ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= fo.off[n_sparse]) return;
+  int lo = 0, hi = n_sparse;                       // field j with off[j] <= i < off[j+1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (fo.off[mid] <= i) lo = mid; else hi = mid;
+  }
+  const int2 key = __ldg(keys + i);
+  const int64_t doc = int64_t(key.y) - doc_id_base;
+  if (key.x < 0 || key.x >= Q || doc < 0 || doc >= n_docs) return;      // other shard / other batch
+  atomicAdd(base + int64_t(key.x) * base_ld + doc, __ldg(w + int64_t(key.x) * w_ld + w_off + lo) * float(vals[i]));
+}
+
+// Vectorised f16 variant: one thread mixes 8 consecutive docs per 16-byte load (n_sparse loads in flight, unrolled
+// by 4), writes two float4.  Needs sparse_ld % 8 == 0 and 16-byte aligned rows (the launcher checks).
+__global__ void sparse_premix_h8_kernel(const uint4* __restrict__ sparse, int64_t ld8, int n_sparse,
+                                        const float* __restrict__ w, int w_ld, int w_off, int64_t n_docs,
+                                        float* __restrict__ base, int64_t base_ld) {
+  const int q = blockIdx.y;
+  const int64_t n8 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;     // group of 8 docs
+  if (n8 * 8 >= n_docs) return;
+  const float* wq = w + int64_t(q) * w_ld + w_off;
+  const uint4* sp = sparse + int64_t(q) * n_sparse * ld8 + n8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int j = 0; j < n_sparse; ++j) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(sp + int64_t(j) * ld8));
+    const float wj = __ldg(wq + j);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      acc[2 * e] = fmaf(wj, f.x, acc[2 * e]);
+      acc[2 * e + 1] = fmaf(wj, f.y, acc[2 * e + 1]);
+    }
+  }
+  float* dst = base + int64_t(q) * base_ld + n8 * 8;                     // base_ld is a multiple of 128: in bounds
+  *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
 // ---------------------------------------------------------------------------------------
 // merge: one CTA (512 threads) per query.  Streams every candidate key of that query from the
 // L lists through a 1024-slot shared buffer: admit keys >= running threshold, and whenever the
@@ -417,9 +470,42 @@ int launch_sparse_premix(const void* sparse, int sparse_dtype, int64_t sparse_ld
   if (sparse_dtype == MFAR_F32)
     sparse_premix_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(sparse), sparse_ld, n_sparse, w, w_ld,
                                                       w_off, n_docs, base, base_ld);
-  else if (sparse_dtype == MFAR_F16)
-    sparse_premix_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(sparse), sparse_ld, n_sparse, w,
-                                                       w_ld, w_off, n_docs, base, base_ld);
+  else if (sparse_dtype == MFAR_F16) {
+    if (sparse_ld % 8 == 0 && reinterpret_cast<uintptr_t>(sparse) % 16 == 0 && base_ld % 8 == 0 &&
+        reinterpret_cast<uintptr_t>(base) % 16 == 0) {
+      dim3 g8((unsigned)(((n_docs + 7) / 8 + 255) / 256), Q);
+      sparse_premix_h8_kernel<<<g8, 256, 0, st>>>(static_cast<const uint4*>(sparse), sparse_ld / 8, n_sparse, w, w_ld,
+                                                  w_off, n_docs, base, base_ld);
+    } else {
+      sparse_premix_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(sparse), sparse_ld, n_sparse, w,
+                                                         w_ld, w_off, n_docs, base, base_ld);
+    }
+  }
+  else
+    return MFAR_ERR_ARG;
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_sparse_premix_coo(const int32_t* keys, const void* vals, int val_dtype, const int64_t* field_offsets_host,
+                             int n_sparse, const float* w, int w_ld, int w_off, int Q, int64_t doc_id_base,
+                             int64_t n_docs, float* base, int64_t base_ld, cudaStream_t st) {
+  CooFieldOffsets fo{};
+  for (int j = 0; j <= n_sparse; ++j) {
+    fo.off[j] = field_offsets_host[j];
+    if (j > 0 && fo.off[j] < fo.off[j - 1]) return MFAR_ERR_ARG;
+  }
+  const long long nnz = fo.off[n_sparse];
+  if (nnz == 0) return MFAR_OK;
+  const unsigned blocks = unsigned((nnz + 255) / 256);
+  if (val_dtype == MFAR_F16)
+    sparse_premix_coo_kernel<__half><<<blocks, 256, 0, st>>>(reinterpret_cast<const int2*>(keys),
+                                                             static_cast<const __half*>(vals), fo, n_sparse, w, w_ld,
+                                                             w_off, Q, doc_id_base, n_docs, base, base_ld);
+  else if (val_dtype == MFAR_F32)
+    sparse_premix_coo_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const int2*>(keys),
+                                                            static_cast<const float*>(vals), fo, n_sparse, w, w_ld,
+                                                            w_off, Q, doc_id_base, n_docs, base, base_ld);
   else
     return MFAR_ERR_ARG;
   MFAR_CUDA_OK(cudaGetLastError());

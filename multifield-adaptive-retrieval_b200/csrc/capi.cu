@@ -151,17 +151,27 @@ size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_spars
   return total;
 }
 
-int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
-                    const void* q_vecs, int Q, const float* w, const void* sparse, int n_sparse, int sparse_dtype,
-                    int64_t sparse_ld, int64_t doc_id_base, int k, uint64_t* out_keys, float* out_scores,
-                    int64_t* out_ids, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+// precomputed per-field sparse scores: dense [Q,Fs,ld] or COO (query row, global doc row, value) grouped by field
+struct SparseInput {
+  int kind = 0;                       // 0 none, 1 dense, 2 COO
+  const void* dense = nullptr; int dense_dtype = MFAR_F16; int64_t dense_ld = 0;
+  const int32_t* coo_keys = nullptr; const void* coo_vals = nullptr; int coo_dtype = MFAR_F16;
+  const int64_t* field_offsets_host = nullptr;
+};
+
+static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
+                           const void* q_vecs, int Q, const float* w, const SparseInput& sp, int n_sparse,
+                           int64_t doc_id_base, int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
+                           void* workspace, size_t workspace_bytes, int impl, void* stream) {
   t_last_launches = 0;
   if (n_docs <= 0 || Q <= 0 || !w || !workspace || (!out_scores && !out_ids && !out_keys)) return MFAR_ERR_ARG;
   if (n_dense < 0 || n_sparse < 0 || n_dense + n_sparse <= 0 || n_dense + n_sparse > MFAR_MAX_FIELDS)
     return MFAR_ERR_SHAPE;
   if (n_dense > 0 && (!corpus || !q_vecs || dim <= 0 || field_begin < 0 || field_begin + n_dense > corpus_fields))
     return MFAR_ERR_ARG;
-  if (n_sparse > 0 && (!sparse || sparse_ld < n_docs)) return MFAR_ERR_ARG;
+  if (n_sparse > 0 && sp.kind == 1 && (!sp.dense || sp.dense_ld < n_docs)) return MFAR_ERR_ARG;
+  if (n_sparse > 0 && sp.kind == 2 && (!sp.field_offsets_host || sp.field_offsets_host[0] != 0)) return MFAR_ERR_ARG;
+  if (n_sparse > 0 && sp.kind == 0) return MFAR_ERR_ARG;
   if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
   if (doc_id_base < 0 || doc_id_base + n_docs > (int64_t(1) << 32)) return MFAR_ERR_SHAPE;
   if (impl < MFAR_IMPL_AUTO || impl > MFAR_IMPL_TCGEN05_QS) return MFAR_ERR_ARG;
@@ -184,10 +194,18 @@ int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int f
 
   if (n_sparse > 0) {
     float* base = reinterpret_cast<float*>(static_cast<char*>(workspace) + ws_topk);
-    if (int rc = launch_sparse_premix(sparse, sparse_dtype, sparse_ld, n_sparse, w, a.w_ld, n_dense, Q, n_docs, base,
-                                      base_ld, st))
-      return rc;
-    ++t_last_launches;
+    if (sp.kind == 1) {
+      if (int rc = launch_sparse_premix(sp.dense, sp.dense_dtype, sp.dense_ld, n_sparse, w, a.w_ld, n_dense, Q, n_docs,
+                                        base, base_ld, st))
+        return rc;
+      ++t_last_launches;
+    } else {
+      MFAR_CUDA_OK(cudaMemsetAsync(base, 0, size_t(Q) * base_ld * 4, st));
+      if (int rc = launch_sparse_premix_coo(sp.coo_keys, sp.coo_vals, sp.coo_dtype, sp.field_offsets_host, n_sparse, w,
+                                            a.w_ld, n_dense, Q, doc_id_base, n_docs, base, base_ld, st))
+        return rc;
+      t_last_launches += 2;
+    }
     a.base = base;
     a.base_ld = base_ld;
   }
@@ -209,6 +227,31 @@ int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int f
   if (rc) return rc;
   ++t_last_launches;
   return MFAR_OK;
+}
+
+
+int mfar_score_topk(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
+                    const void* q_vecs, int Q, const float* w, const void* sparse, int n_sparse, int sparse_dtype,
+                    int64_t sparse_ld, int64_t doc_id_base, int k, uint64_t* out_keys, float* out_scores,
+                    int64_t* out_ids, void* workspace, size_t workspace_bytes, int impl, void* stream) {
+  SparseInput sp;
+  if (n_sparse > 0) { sp.kind = 1; sp.dense = sparse; sp.dense_dtype = sparse_dtype; sp.dense_ld = sparse_ld; }
+  return score_topk_core(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, q_vecs, Q, w, sp, n_sparse,
+                         doc_id_base, k, out_keys, out_scores, out_ids, workspace, workspace_bytes, impl, stream);
+}
+
+int mfar_score_topk_coo(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
+                        const void* q_vecs, int Q, const float* w, const int32_t* coo_keys, const void* coo_vals,
+                        int coo_dtype, const int64_t* field_offsets_host, int n_sparse, int64_t doc_id_base, int k,
+                        uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* workspace,
+                        size_t workspace_bytes, int impl, void* stream) {
+  if (n_sparse <= 0 || !field_offsets_host) return MFAR_ERR_ARG;
+  if (field_offsets_host[n_sparse] > 0 && (!coo_keys || !coo_vals)) return MFAR_ERR_ARG;
+  SparseInput sp;
+  sp.kind = 2; sp.coo_keys = coo_keys; sp.coo_vals = coo_vals; sp.coo_dtype = coo_dtype;
+  sp.field_offsets_host = field_offsets_host;
+  return score_topk_core(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, q_vecs, Q, w, sp, n_sparse,
+                         doc_id_base, k, out_keys, out_scores, out_ids, workspace, workspace_bytes, impl, stream);
 }
 
 int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_t* out_keys, float* out_scores,

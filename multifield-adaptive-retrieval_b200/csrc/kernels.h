@@ -19,6 +19,9 @@ int launch_score_candidates(const void* corpus, int64_t n_docs, int corpus_field
 int launch_sparse_premix(const void* sparse, int sparse_dtype, int64_t sparse_ld, int n_sparse, const float* w,
                          int w_ld, int w_off, int Q, int64_t n_docs, float* base, int64_t base_ld,
                          cudaStream_t st);
+int launch_sparse_premix_coo(const int32_t* keys, const void* vals, int val_dtype, const int64_t* field_offsets_host,
+                             int n_sparse, const float* w, int w_ld, int w_off, int Q, int64_t doc_id_base,
+                             int64_t n_docs, float* base, int64_t base_ld, cudaStream_t st);
 int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
                  int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
 int launch_zero_init(float* scores, int64_t* ids, int n, cudaStream_t st);

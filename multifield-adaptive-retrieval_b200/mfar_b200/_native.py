@@ -34,6 +34,8 @@ PROTOTYPES = {
     "mfar_score_topk_workspace_bytes": (_sz, [_i, _i, _i64, _i]),
     "mfar_score_topk": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i64, _i64, _i, _vp, _vp, _vp,
                              _vp, _sz, _i, _vp]),
+    "mfar_score_topk_coo": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _i, _i64, _i, _vp, _vp, _vp,
+                                 _vp, _sz, _i, _vp]),
     "mfar_topk_merge": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mfar_exchange_buffer_bytes": (_sz, [_i, _i, _i]),
     "mfar_topk_exchange_merge": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

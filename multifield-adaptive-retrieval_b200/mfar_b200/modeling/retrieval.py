@@ -161,15 +161,15 @@ class MultiFieldRetriever:
         if sparse is None:
             raise ValueError(f"retriever has {self.n_sparse} sparse fields: pass their precomputed scores [Q,Fs,N]")
         nv.require_device(sparse, "sparse")
-        if tuple(sparse.shape) != (Q, self.n_sparse, self.n_docs):
-            raise ValueError(f"sparse must be [{Q},{self.n_sparse},{self.n_docs}], got {tuple(sparse.shape)}")
+        if sparse.dim() != 3 or tuple(sparse.shape[:2]) != (Q, self.n_sparse) or sparse.shape[2] < self.n_docs:
+            raise ValueError(f"sparse must be [{Q},{self.n_sparse},>={self.n_docs}], got {tuple(sparse.shape)}")
         if sparse.dtype not in (torch.float16, torch.float32):
             sparse = sparse.float()
         return sparse.contiguous(), (nv.F16 if sparse.dtype == torch.float16 else nv.F32)
 
     def _score_topk(self, q_bf16: Optional[torch.Tensor], w: torch.Tensor, sparse, sparse_code: int, k: int,
                     field_begin: int, n_dense: int, n_sparse: int, want_keys: bool = False, impl: Optional[str] = None,
-                    n_docs: Optional[int] = None, doc_id_base: Optional[int] = None):
+                    n_docs: Optional[int] = None, doc_id_base: Optional[int] = None, sparse_coo=None):
         Q = w.shape[0]
         n_docs = self.n_docs if n_docs is None else n_docs
         doc_id_base = self.doc_id_base if doc_id_base is None else doc_id_base
@@ -180,10 +180,23 @@ class MultiFieldRetriever:
         keys = torch.empty((Q, k), dtype=torch.int64, device=self.device) if want_keys else None
         ws = self._workspace(Q, k, n_sparse, n_docs)
         c = self.corpus
+        if sparse_coo is not None:
+            import ctypes
+            coo_keys, coo_vals, offsets = sparse_coo
+            off = (ctypes.c_int64 * (n_sparse + 1))(*[int(x) for x in offsets])
+            nv.check(nv.lib().mfar_score_topk_coo(
+                nv.ptr(c.data) if c is not None else 0, n_docs, c.n_fields if c is not None else 0, field_begin,
+                n_dense, c.dim_pad if c is not None else 0, nv.ptr(q_bf16), Q, nv.ptr(w), nv.ptr(coo_keys),
+                nv.ptr(coo_vals), nv.F16 if coo_vals.dtype == torch.float16 else nv.F32, ctypes.addressof(off), n_sparse,
+                doc_id_base, k, nv.ptr(keys), nv.ptr(scores), nv.ptr(ids), nv.ptr(ws), ws.numel(),
+                nv.IMPL[impl or self.impl], nv.stream()), "score_topk_coo")
+            self.last_launches = nv.lib().mfar_last_launch_count()
+            return scores, ids, keys
         nv.check(nv.lib().mfar_score_topk(
             nv.ptr(c.data) if c is not None else 0, n_docs, c.n_fields if c is not None else 0, field_begin,
             n_dense, c.dim_pad if c is not None else 0, nv.ptr(q_bf16), Q, nv.ptr(w), nv.ptr(sparse), n_sparse,
-            sparse_code, n_docs, doc_id_base, k, nv.ptr(keys), nv.ptr(scores), nv.ptr(ids), nv.ptr(ws),
+            sparse_code, (sparse.shape[2] if sparse is not None else n_docs), doc_id_base, k, nv.ptr(keys),
+            nv.ptr(scores), nv.ptr(ids), nv.ptr(ws),
             ws.numel(), nv.IMPL[impl or self.impl], nv.stream()), "score_topk")
         self.last_launches = nv.lib().mfar_last_launch_count()
         return scores, ids, keys
@@ -191,13 +204,17 @@ class MultiFieldRetriever:
     # ------------------------------------------------------------------ exhaustive fused search
     @torch.no_grad()
     def search(self, q_vecs, q_emb: Optional[torch.Tensor] = None, sparse: Optional[torch.Tensor] = None,
-               top_k: Optional[int] = None, return_keys: bool = False, impl: Optional[str] = None):
+               top_k: Optional[int] = None, return_keys: bool = False, impl: Optional[str] = None, sparse_coo=None):
         """Exhaustive multi-field top-k.
 
         q_vecs [Q,dim]: query vectors for the dense dots (rounded to bf16);
         q_emb  [Q,E]  : fp32 query embedding for the mixture softmax (defaults to q_vecs, as in the
                         reference where both come from the same encoder, contrastive.py:688-694);
-        sparse [Q,Fs,N]: precomputed per-field BM25 scores of this shard's docs (f16/f32).
+        sparse [Q,Fs,ld>=N]: precomputed per-field BM25 scores of this shard's docs (f16/f32); a row pitch ``ld``
+                        that is a multiple of 8 lets the f16 pre-mix kernel use 16-byte loads.
+        sparse_coo     : instead of ``sparse``: (keys int32 [nnz,2] = (query row, GLOBAL doc row), vals f16/f32 [nnz],
+                        field_offsets [Fs+1]) on the device - the reference's precomputed-BM25 layout
+                        (``PrecomputedSparseScores.batch``); pairs that are absent score 0 (index.py:120-125).
         Returns (scores [Q,k] fp32, ids [Q,k] int64) sorted by (score desc, id asc); with
         return_keys also the packed uint64 keys (as int64) used for cross-shard merging."""
         k = top_k or self.top_k
@@ -205,13 +222,28 @@ class MultiFieldRetriever:
             q_bf16 = self.corpus.prepare_queries(q_vecs)
             Q = q_bf16.shape[0]
         else:
-            q_bf16, Q = None, sparse.shape[0]
+            q_bf16, Q = None, (sparse.shape[0] if sparse is not None else int(q_emb.shape[0]))
         if self.mixture.query_cond:
             qe = q_emb if q_emb is not None else (q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs))
             qe = qe.to(self.device).float()
         else:
             qe = None
         w = self.mixture.field_weights(qe, self.mask, batch=Q)
+        if sparse_coo is not None:
+            if self.n_sparse == 0:
+                raise ValueError("retriever has no sparse fields")
+            ck, cv, off = sparse_coo
+            nv.require_device(ck, "sparse_coo keys"); nv.require_device(cv, "sparse_coo vals")
+            if ck.dtype != torch.int32 or ck.dim() != 2 or ck.shape[1] != 2 or cv.shape[0] != ck.shape[0]:
+                raise ValueError("sparse_coo keys must be int32 [nnz,2] with one value per row")
+            if len(off) != self.n_sparse + 1 or int(off[-1]) != ck.shape[0]:
+                raise ValueError("field_offsets must have n_sparse+1 entries ending at nnz")
+            if cv.dtype not in (torch.float16, torch.float32):
+                cv = cv.float()
+            scores, ids, keys = self._score_topk(q_bf16, w, None, nv.F16, k, 0, self.n_dense, self.n_sparse,
+                                                 want_keys=return_keys, impl=impl,
+                                                 sparse_coo=(ck.contiguous(), cv.contiguous(), off))
+            return (scores, ids, keys) if return_keys else (scores, ids)
         sp, code = self._check_sparse(sparse, Q)
         scores, ids, keys = self._score_topk(q_bf16, w, sp, code, k, 0, self.n_dense, self.n_sparse,
                                              want_keys=return_keys, impl=impl)
@@ -236,6 +268,8 @@ class MultiFieldRetriever:
             raise ValueError("q_emb_host must be a host fp32 [Q,E] tensor")
         code = nv.F16
         if self.n_sparse:
+            if tuple(sparse_host.shape) != (Q, self.n_sparse, self.n_docs) or not sparse_host.is_contiguous():
+                raise ValueError(f"sparse_host must be a contiguous [{Q},{self.n_sparse},{self.n_docs}] host tensor")
             code = nv.F16 if sparse_host.dtype == torch.float16 else nv.F32
         need = nv.lib().mfar_search_host_scratch_bytes(Q, c.dim_pad if c else 0, E, self.n_dense, self.n_sparse,
                                                        self.n_docs, code, k)

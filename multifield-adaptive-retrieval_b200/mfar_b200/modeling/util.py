@@ -24,6 +24,60 @@ def read_corpus(path: str) -> Iterable[Tuple[str, object]]:
                     yield row[0], row[1]
 
 
+class PrecomputedSparseScores:
+    """Precomputed per-field BM25 scores in the reference's file layout
+    (``{scores_path}/{field_key}_keys_bm25.npy`` int32 [nnz,2] = (query id, doc row) and
+    ``{field_key}_vals_bm25.npy`` float16 [nnz]; written by mfar/commands/precompute_bm25s_scores.py:21-30, read by
+    ``read_sparse_scores``, mfar/modeling/util.py:151-173).  Instead of the reference's nested Python dicts the
+    pairs stay as arrays sorted by query id; ``batch(query_ids)`` slices out the pairs of one query batch in the
+    COO form ``MultiFieldRetriever.search(sparse_coo=...)`` consumes."""
+
+    def __init__(self, per_field: Dict[str, Tuple["np.ndarray", "np.ndarray"]], field_keys: List[str]):
+        import numpy as np
+        self.field_keys = list(field_keys)
+        self._f = {}
+        for fk in self.field_keys:
+            keys, vals = per_field[fk]
+            keys = np.asarray(keys, dtype=np.int32).reshape(-1, 2)
+            vals = np.asarray(vals)
+            assert len(keys) == len(vals)                              # modeling/util.py:163
+            order = np.argsort(keys[:, 0], kind="stable")
+            self._f[fk] = (np.ascontiguousarray(keys[order, 0]), np.ascontiguousarray(keys[order, 1]),
+                           np.ascontiguousarray(vals[order]))
+
+    @classmethod
+    def load(cls, scores_path: str, field_info: Dict[str, Field]) -> "PrecomputedSparseScores":
+        import numpy as np
+        sparse = [k for k, f in field_info.items() if f.field_type == FieldType.SPARSE]
+        return cls({k: (np.load(f"{scores_path}/{k}_keys_bm25.npy"), np.load(f"{scores_path}/{k}_vals_bm25.npy"))
+                    for k in sparse}, sparse)
+
+    def lookup(self, field_key: str, qid: int, doc_row: int) -> float:
+        """``sparse_scores[field].get(qid, {}).get(doc, 0)`` of the reference (index.py:120-125)."""
+        import numpy as np
+        q, d, v = self._f[field_key]
+        lo, hi = np.searchsorted(q, qid, "left"), np.searchsorted(q, qid, "right")
+        hit = np.nonzero(d[lo:hi] == doc_row)[0]
+        return float(v[lo + hit[-1]]) if len(hit) else 0.0             # dict semantics: the last duplicate wins
+
+    def batch(self, query_ids, device="cuda"):
+        """-> (keys int32 [nnz,2] (row in batch, doc row), vals [nnz], field_offsets [Fs+1]) on ``device``."""
+        import numpy as np
+        import torch
+        ks, vs, offs = [], [], [0]
+        for fk in self.field_keys:
+            q, d, v = self._f[fk]
+            for row, qid in enumerate(query_ids):
+                lo, hi = np.searchsorted(q, qid, "left"), np.searchsorted(q, qid, "right")
+                if hi > lo:
+                    ks.append(np.stack([np.full(hi - lo, row, np.int32), d[lo:hi]], axis=1))
+                    vs.append(v[lo:hi])
+            offs.append(sum(len(x) for x in vs))
+        keys = np.concatenate(ks) if ks else np.zeros((0, 2), np.int32)
+        vals = np.concatenate(vs) if vs else np.zeros((0,), np.float16)
+        return torch.from_numpy(keys).to(device), torch.from_numpy(vals).to(device), offs
+
+
 def read_and_create_indices(corpus_path: str, dataset_name: str, field_info: Dict[str, Field], temp_dir: str,
                             encoder, device="cuda", sparse_scores: Optional[Dict[str, Dict[str, object]]] = None):
     """Same contract as the reference (modeling/util.py:73-108): returns

@@ -50,9 +50,16 @@ def make_mixture(dim: int, F: int, seed: int, query_cond: bool = True, device="c
     return torch.randn((F, 1), generator=g).to(device)
 
 
-def make_sparse(Q: int, Fs: int, n_docs: int, seed: int, device="cpu", dtype=torch.float16) -> Optional[torch.Tensor]:
+def make_sparse(Q: int, Fs: int, n_docs: int, seed: int, device="cpu", dtype=torch.float16,
+                pitch: int = 1) -> Optional[torch.Tensor]:
+    """[Q, Fs, ld] with ld = n_docs rounded up to ``pitch`` (columns beyond n_docs are zero)."""
     if Fs == 0:
         return None
+    if pitch > 1 and n_docs % pitch:
+        ld = (n_docs + pitch - 1) // pitch * pitch
+        out = torch.zeros((Q, Fs, ld), dtype=dtype, device=device)
+        out[:, :, :n_docs] = make_sparse(Q, Fs, n_docs, seed, device, dtype)
+        return out
     g = _gen(device, seed)
     u = torch.rand((Q, Fs, n_docs), generator=g, device=device)
     # Gamma(2, scale 2) = sum of two Exp(scale 2)

@@ -321,6 +321,42 @@ def test_virtual_shards_merge_equals_single_shard(impl):
         assert torch.equal(i, i0) and torch.equal(s, s0), R
 
 
+@pytest.mark.parametrize("impl", IMPLS)
+def test_sparse_coo_input_equals_dense_input_and_oracle(impl, tmp_path):
+    """Sparse scores given in the reference's precomputed-BM25 file layout (int32 (qid, doc) pairs + f16 values per
+    field, precompute_bm25s_scores.py:21-30) vs the same scores as a dense [Q,Fs,N] tensor vs the oracle; a sharded
+    retriever must skip the pairs of other shards."""
+    from mfar_b200.data.typedef import Field, FieldType
+    from mfar_b200.modeling.util import PrecomputedSparseScores
+    seed, N, d, Fd, Fs, Q, k = 41, 1500, 128, 2, 3, 7, 50
+    fields, q, sp, W = synth(seed, N, d, Fd, Fs, Q, True)
+    qids = [1000 + 7 * i for i in range(Q)]
+    finfo = {f"s{j}_sparse": Field(f"s{j}_sparse", f"s{j}", FieldType.SPARSE) for j in range(Fs)}
+    for j, fk in enumerate(finfo):                                     # write the files the reference would
+        nz = torch.nonzero(sp[:, j, :])
+        order = torch.randperm(len(nz), generator=torch.Generator().manual_seed(j))
+        nz = nz[order]
+        keys = np.stack([np.array(qids)[nz[:, 0].numpy()], nz[:, 1].numpy()], axis=1).astype(np.int32)
+        np.save(tmp_path / f"{fk}_keys_bm25.npy", keys)
+        np.save(tmp_path / f"{fk}_vals_bm25.npy", sp[nz[:, 0], j, nz[:, 1]].numpy().astype(np.float16))
+    store = PrecomputedSparseScores.load(str(tmp_path), finfo)
+    assert store.lookup("s1_sparse", qids[2], int(torch.nonzero(sp[2, 1])[0])) == float(sp[2, 1, torch.nonzero(sp[2, 1])[0]])
+    assert store.lookup("s1_sparse", qids[2], int(torch.nonzero(sp[2, 1] == 0)[0])) == 0.0
+    coo = store.batch(qids, DEV)
+    if impl == "simt" or Fd:
+        r = build(fields, W, True, Fs, k, impl=impl)
+        s_coo, i_coo = r.search(q.to(DEV), q.to(DEV), sparse_coo=coo)
+        s_dense, i_dense = r.search(q.to(DEV), q.to(DEV), sp.to(DEV))
+        torch.testing.assert_close(s_coo, s_dense, rtol=1e-6, atol=1e-5)
+        assert (i_coo == i_dense).float().mean().item() > 0.99
+        ref = O.exhaustive_scores(q, fields, sp.float(), O.mixture_weights(q, W, True))
+        assert_topk_parity(s_coo.cpu().numpy(), i_coo.cpu().numpy(), ref.numpy(), k)
+        lo, hi = 512, 1100                                             # a shard: global doc rows [lo, hi)
+        sh = build([f[lo:hi] for f in fields], W, True, Fs, k, doc_id_base=lo, impl=impl)
+        s_sh, i_sh = sh.search(q.to(DEV), q.to(DEV), sparse_coo=coo)
+        assert_topk_parity(s_sh.cpu().numpy(), i_sh.cpu().numpy(), ref[:, lo:hi].numpy(), k, id_offset=lo)
+
+
 def test_peer_exchange_merge_virtual_ranks():
     """The fused NVLink exchange+merge kernel with R "virtual ranks" on one device: R exchange buffers, R concurrent
     streams, each rank pushing into all buffers and spinning on its own flags.  Three epochs (both parities and a
