@@ -1,5 +1,7 @@
 // Corpus pack/unpack, field-mixture weights, candidate re-scoring, sparse pre-mix and the
 // top-k merge.  All small / bandwidth-trivial next to the scoring pass; plain CUDA-core code.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -210,31 +212,81 @@ __global__ void sparse_premix_h8_kernel(const uint4* __restrict__ sparse, int64_
 constexpr int kMergeThreads = 512;
 constexpr int kMergeBuf = 1024;
 
-__device__ __forceinline__ void block_sort1024_desc(uint64_t* buf) {
-  for (int s = 2; s <= kMergeBuf; s <<= 1) {
+// block bitonic sort, descending, of the first n (power of two, <= kMergeBuf) slots
+__device__ __forceinline__ void block_sort_desc(uint64_t* buf, int n) {
+  for (int s = 2; s <= n; s <<= 1) {
     for (int d = s >> 1; d > 0; d >>= 1) {
       __syncthreads();
-      const int t = threadIdx.x;                       // 512 compare-exchanges per stage
-      const int lo = ((t & ~(d - 1)) << 1) | (t & (d - 1));
-      const int hi = lo | d;
-      const bool desc = (lo & s) == 0 || s == kMergeBuf;
-      uint64_t a = buf[lo], b = buf[hi];
-      if ((a < b) == desc) { buf[lo] = b; buf[hi] = a; }
+      const int t = threadIdx.x;                       // n/2 compare-exchanges per stage
+      if (t < (n >> 1)) {
+        const int lo = ((t & ~(d - 1)) << 1) | (t & (d - 1));
+        const int hi = lo | d;
+        const bool desc = (lo & s) == 0 || s == n;
+        uint64_t a = buf[lo], b = buf[hi];
+        if ((a < b) == desc) { buf[lo] = b; buf[hi] = a; }
+      }
     }
   }
   __syncthreads();
 }
+__device__ __forceinline__ void block_sort1024_desc(uint64_t* buf) { block_sort_desc(buf, kMergeBuf); }
+__device__ __forceinline__ int pow2_at_least(int c, int floor_) {
+  int n = floor_;
+  while (n < c) n <<= 1;
+  return n;
+}
+
+// A many-list merge sees ~L*k candidates above the best per-list threshold (a CTA's k-th key is a weak bound
+// shard-wide: ~L*k docs beat it), far more than the 1024-slot sort buffer.  So:
+//   A. sweep the lists (a warp per list, coalesced, valid entries only), keep the 32-bit SCORE WORD of every key
+//      >= max-threshold in dynamic shared memory (sc_cap words);
+//   B. binary-search those words for a cut T with k <= count(score >= T) <= 1024 (one shared-memory pass + block
+//      count per probe, ~12 probes);
+//   C. sweep the lists again (L2 hits), gather the full keys with score >= T, bitonic-sort, emit the top k.
+// If A overflows sc_cap the kernel falls back to the streaming path (stream through the 1024-slot buffer, sort,
+// raise the threshold, repeat).
+template <class F>
+__device__ __forceinline__ void merge_sweep(const uint64_t* __restrict__ keys, const int* __restrict__ counts, int L,
+                                            int q_stride, int slots, int q, F&& f) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31, nwarp = kMergeThreads >> 5;
+  for (int l0 = warp; l0 < L; l0 += nwarp * 4) {
+    int cnt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * nwarp;
+      cnt[u] = (l < L) ? (counts ? __ldg(counts + int64_t(l) * q_stride + q) : slots) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int l = l0 + u * nwarp;
+      const uint64_t* list = keys + (int64_t(l) * q_stride + q) * slots;
+      for (int s0 = 0; s0 < cnt[u]; s0 += 256) {
+        uint64_t key[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int sl = s0 + j * 32 + lane;
+          key[j] = (sl < cnt[u]) ? __ldcg(list + sl) : 0ull;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (key[j] != 0ull) f(key[j]);
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, const uint64_t* __restrict__ thr,
-             int L, int q_stride, int slots, int k, uint64_t* __restrict__ out_keys,
+             int L, int q_stride, int slots, int k, int sc_cap, uint64_t* __restrict__ out_keys,
              float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  extern __shared__ uint32_t sc[];                     // [sc_cap] score words of the candidates
   __shared__ uint64_t buf[kMergeBuf];
-  __shared__ int s_cnt;
+  __shared__ int s_cnt, s_probe;
+  __shared__ unsigned int s_max;
   __shared__ unsigned long long s_thr;
   const int q = blockIdx.x;
   const int t = threadIdx.x;
-  if (t == 0) { s_cnt = 0; s_thr = 0ull; }
+  if (t == 0) { s_cnt = 0; s_thr = 0ull; s_max = 0u; s_probe = 0; }
   __syncthreads();
   if (thr != nullptr) {                                // a list that was compacted holds >= k keys >= its thr
     unsigned long long m = 0ull;
@@ -245,35 +297,55 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
     if (m) atomicMax(&s_thr, m);
   }
   __syncthreads();
-  const int64_t total = int64_t(L) * slots;
-  // ---- fast path: one sync-free sweep with independent (unrolled) loads.  After the threshold filter the survivors
-  // of a many-list merge normally fit the buffer; if they do not, fall through to the streaming path below.
+  // ---- A: score words of everything above the threshold
   {
-    constexpr int kUnroll = 8;
-    for (int64_t base = 0; base < total; base += int64_t(kMergeThreads) * kUnroll) {
-      uint64_t key[kUnroll];
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j) {
-        const int64_t i = base + int64_t(j) * kMergeThreads + t;
-        key[j] = 0ull;
-        if (i < total) {
-          const int l = int(i / slots), sl = int(i % slots);
-          const int cnt = counts ? __ldg(counts + int64_t(l) * q_stride + q) : slots;
-          if (sl < cnt) key[j] = __ldcg(keys + (int64_t(l) * q_stride + q) * slots + sl);
-        }
+    const unsigned long long thr0 = s_thr;
+    unsigned int mx = 0u;
+    merge_sweep(keys, counts, L, q_stride, slots, q, [&](uint64_t key) {
+      if (key >= thr0) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        const uint32_t w = uint32_t(key >> 32);
+        if (pos < sc_cap) sc[pos] = w;
+        mx = w > mx ? w : mx;
       }
-#pragma unroll
-      for (int j = 0; j < kUnroll; ++j)
-        if (key[j] != 0ull && key[j] >= s_thr) {
-          const int pos = atomicAdd(&s_cnt, 1);
-          if (pos < kMergeBuf) buf[pos] = key[j];
-        }
+    });
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((t & 31) == 0 && mx) atomicMax(&s_max, mx);
+  }
+  __syncthreads();
+  const int c = s_cnt;
+  if (c <= sc_cap) {
+    // ---- B: cut T with k <= count(score >= T) <= kMergeBuf (score ties can make that impossible: then the widest
+    // count above kMergeBuf falls back to streaming below)
+    uint32_t lo = uint32_t(s_thr >> 32), up = s_max;   // count(>= lo) = c; answer in [lo, up]
+    int c_lo = c;
+    while (c_lo > kMergeBuf && lo < up) {
+      const uint32_t mid = lo + ((up - lo + 1u) >> 1);
+      int n = 0;
+      for (int i = t; i < c; i += kMergeThreads) n += (sc[i] >= mid) ? 1 : 0;
+      n = __reduce_add_sync(0xffffffffu, n);
+      __syncthreads();                                 // everyone has read s_probe's previous value
+      if (t == 0) s_probe = 0;
+      __syncthreads();
+      if ((t & 31) == 0 && n) atomicAdd(&s_probe, n);
+      __syncthreads();
+      const int cm = s_probe;
+      if (cm >= k) { lo = mid; c_lo = cm; } else { up = mid - 1u; }
     }
-    __syncthreads();
-    const int c = s_cnt;
-    if (c <= kMergeBuf) {
-      for (int j = c + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
-      block_sort1024_desc(buf);
+    if (c_lo <= kMergeBuf) {
+      // ---- C: gather the full keys above the cut, sort, emit
+      __syncthreads();
+      if (t == 0) s_cnt = 0;
+      __syncthreads();
+      const unsigned long long thr0 = s_thr;
+      merge_sweep(keys, counts, L, q_stride, slots, q, [&](uint64_t key) {
+        if (key >= thr0 && uint32_t(key >> 32) >= lo) buf[atomicAdd(&s_cnt, 1)] = key;
+      });
+      __syncthreads();
+      const int cc = s_cnt;
+      const int n = pow2_at_least(cc > k ? cc : k, 128);
+      for (int j = cc + t; j < n; j += kMergeThreads) buf[j] = 0ull;
+      block_sort_desc(buf, n);
       for (int j = t; j < k; j += kMergeThreads) {
         const uint64_t key = buf[j];
         if (out_keys) out_keys[int64_t(q) * k + j] = key;
@@ -282,36 +354,37 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
       }
       return;
     }
-    __syncthreads();
-    if (t == 0) s_cnt = 0;
-    __syncthreads();
   }
+  __syncthreads();
+  if (t == 0) s_cnt = 0;
+  __syncthreads();
   // ---- streaming path
-  for (int64_t base = 0; base < total; base += kMergeThreads) {
-    const int64_t i = base + t;
+  const int total = L * slots;
+  for (int base = 0; base < total; base += kMergeThreads) {
+    const int i = base + t;
     if (i < total) {
-      const int l = int(i / slots), s = int(i % slots);
+      const int l = i / slots, sl = i % slots;
       const int cnt = counts ? counts[int64_t(l) * q_stride + q] : slots;
-      if (s < cnt) {
-        const uint64_t key = keys[(int64_t(l) * q_stride + q) * slots + s];
+      if (sl < cnt) {
+        const uint64_t key = keys[(int64_t(l) * q_stride + q) * slots + sl];
         if (key != 0ull && key >= s_thr) buf[atomicAdd(&s_cnt, 1)] = key;
       }
     }
     __syncthreads();
-    const int c = s_cnt;                               // snapshot, then barrier: the branch below must be
+    const int cs = s_cnt;                              // snapshot, then barrier: the branch below must be
     __syncthreads();                                   // uniform even if fast threads start the next round
-    if (c > kMergeBuf - kMergeThreads) {
-      for (int j = c + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
+    if (cs > kMergeBuf - kMergeThreads) {
+      for (int j = cs + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
       block_sort1024_desc(buf);
       if (t == 0) {
-        s_cnt = c < k ? c : k;
-        if (c >= k) s_thr = buf[k - 1];
+        s_cnt = cs < k ? cs : k;
+        if (cs >= k) s_thr = buf[k - 1];
       }
       __syncthreads();
     }
   }
-  const int c = s_cnt;
-  for (int j = c + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
+  const int cs = s_cnt;
+  for (int j = cs + t; j < kMergeBuf; j += kMergeThreads) buf[j] = 0ull;
   block_sort1024_desc(buf);
   for (int j = t; j < k; j += kMergeThreads) {
     const uint64_t key = buf[j];
@@ -514,7 +587,18 @@ int launch_sparse_premix_coo(const int32_t* keys, const void* vals, int val_dtyp
 
 int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
                  int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st) {
-  merge_kernel<<<Q, kMergeThreads, 0, st>>>(keys, counts, thr, L, q_stride, slots, k, out_keys, out_scores, out_ids);
+  if (int64_t(L) * slots > (int64_t(1) << 30)) return MFAR_ERR_SHAPE;
+  // score-word scratch: every slot of every list if that fits ~150 KB, else a cap (overflow -> streaming path)
+  int sc_cap = int(std::min<int64_t>(int64_t(L) * slots, 38 * 1024));
+  sc_cap = (sc_cap + 3) & ~3;
+  const size_t smem = size_t(sc_cap) * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MFAR_CUDA_OK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  merge_kernel<<<Q, kMergeThreads, smem, st>>>(keys, counts, thr, L, q_stride, slots, k, sc_cap, out_keys, out_scores,
+                                              out_ids);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }
