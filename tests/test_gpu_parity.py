@@ -215,6 +215,60 @@ def test_query_stationary_agrees_with_doc_stationary_at_scale():
     assert (i1 == i2).float().mean().item() > 0.98
 
 
+def test_full_size_properties_10m_docs():
+    """BASELINE.json config 5 at FULL size (10M docs x 8 fields x 768, 122.9 GB resident) - far beyond what the CPU
+    oracle can score, so size-independent properties: (a) the three kernels agree (batch-4 doc-stationary, batch-70
+    query-stationary single CTA, batch-140 CTA pairs) on the queries they share; (b) sorted, unique, in-range ids;
+    (c) doc-range shards merged with the merge kernel reproduce the unsharded result bit for bit; (d) the winners'
+    scores equal the oracle's fp32 re-computation from the stored vectors."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 140e9:
+        pytest.skip("needs ~125 GB of free HBM")
+    MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    from mfar_b200 import synth as S
+    from mfar_b200.dist import merge_keys
+    N, F, d, k = 10_000_000, 8, 768, 100
+    pc = PackedCorpus(N, F, d, DEV)
+    S.fill_packed_corpus(pc, seed=1234)
+    mu = S.corpus_mean(d, 1234, DEV)
+    q = S.make_queries(140, d, mu, 77, DEV)
+    layer = LinearWeights(d, F, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(S.make_mixture(d, F, 78))
+    r = MultiFieldRetriever(pc, layer.to(DEV), top_k=k)
+    s_a, i_a = r.search(q[:4], q[:4].float(), impl="tcgen05")
+    s_b, i_b = r.search(q[:70], q[:70].float(), impl="tcgen05_qs")
+    s_c, i_c, keys_c = r.search(q, q.float(), impl="auto", return_keys=True)
+    for s_, i_ in ((s_a, i_a), (s_b, i_b), (s_c, i_c)):
+        assert (s_[:, :-1] >= s_[:, 1:]).all()
+        assert i_.min() >= 0 and i_.max() < N
+        assert all(len(set(row.tolist())) == k for row in i_.cpu())
+    torch.testing.assert_close(s_a, s_c[:4], rtol=2e-5, atol=1e-4)
+    torch.testing.assert_close(s_b, s_c[:70], rtol=2e-5, atol=1e-4)
+    assert (i_a == i_c[:4]).float().mean().item() > 0.98 and (i_b == i_c[:70]).float().mean().item() > 0.98
+    # (c) two virtual shards over the same packed corpus (tile-aligned split), merged
+    cut = 128 * 40_000
+    parts = []
+    for lo, hi in ((0, cut), (cut, N)):
+        view = PackedCorpus.__new__(PackedCorpus)
+        view.device, view.n_docs, view.n_fields, view.dim, view.dim_pad, view.normalize = pc.device, hi - lo, F, d, pc.dim_pad, False
+        view.data = pc.data[(lo // 128) * F * 128 * pc.dim_pad:]
+        sh = MultiFieldRetriever(view, layer, top_k=k, doc_id_base=lo)
+        parts.append(sh.search(q, q.float(), return_keys=True)[2])
+    s_m, i_m = merge_keys(torch.stack(parts), k)
+    assert torch.equal(i_m, i_c) and torch.equal(s_m, s_c)
+    # (d) oracle re-computation of the winners of two queries
+    for qi in (0, 139):
+        rows = i_c[qi]
+        per_field = torch.stack([torch.stack([pc.unpack_field(f, int(x), 1)[0] for x in rows.tolist()])
+                                 for f in range(F)]).cpu()                                       # [F,k,d]
+        w = O.mixture_weights(q[qi:qi + 1].float().cpu(), layer.weight.cpu(), True)[0]
+        ref = sum(w[f] * (per_field[f] @ q[qi].float().cpu()) for f in range(F))
+        torch.testing.assert_close(s_c[qi].cpu(), ref, rtol=2e-5, atol=1e-4)
+    del pc, r, parts
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[:-4] for p in CASES])
 def test_per_field_topk_vs_reference_retrieve_batch(path):
     """DenseFlatIndex.retrieve_batch incl. the (0.0, row 0) running-top-k init (index.py:192-193)."""
