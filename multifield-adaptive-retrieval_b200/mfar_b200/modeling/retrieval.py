@@ -249,6 +249,62 @@ class MultiFieldRetriever:
                                              want_keys=return_keys, impl=impl)
         return (scores, ids, keys) if return_keys else (scores, ids)
 
+    # ------------------------------------------------------------------ field-masking sweep in one corpus pass
+    @staticmethod
+    def mask_sweep_plan(field_info) -> List[Tuple[str, List[int]]]:
+        """The evaluations ``mask_fields`` runs one after another, each a full pass with the corpus re-encoded
+        (mfar/commands/mask_fields.py:142-170): baseline, every single field, all sparse, all dense, every field name.
+        Returns (label, masked field indices) in that order (names sorted; the reference iterates a set)."""
+        from ..data.typedef import FieldType
+        fields = list(field_info.values())
+        plan: List[Tuple[str, List[int]]] = [("baseline", [])]
+        plan += [(f"field:{k}", [i]) for i, k in enumerate(field_info.keys())]
+        sparse_idx = [i for i, f in enumerate(fields) if f.field_type == FieldType.SPARSE]
+        dense_idx = [i for i, f in enumerate(fields) if f.field_type == FieldType.DENSE]
+        if sparse_idx:
+            plan.append(("all_sparse", sparse_idx))
+        if dense_idx:
+            plan.append(("all_dense", dense_idx))
+        for name in sorted({f.name for f in fields}):
+            plan.append((f"name:{name}", [i for i, f in enumerate(fields) if f.name == name]))
+        return plan
+
+    @torch.no_grad()
+    def search_mask_sweep(self, q_vecs, masked_sets: Sequence[Sequence[int]], q_emb: Optional[torch.Tensor] = None,
+                          sparse: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
+                          max_rows: int = 1024) -> Tuple[torch.Tensor, torch.Tensor]:
+        """All M maskings of ``mask_field`` evaluated as extra weight rows of ONE fused pass per chunk: the mask only
+        multiplies the softmax weights (contrastive.py:686, no renormalisation), so masking m of query q is the
+        pseudo-query (q, w[q] * mask_m).  Returns (scores [M,Q,k], ids [M,Q,k]).  Rows are processed in chunks of
+        at most ``max_rows`` pseudo-queries; dense sparse-score tensors are repeated per chunk."""
+        k = top_k or self.top_k
+        q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
+        Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
+        if self.mixture.query_cond:
+            qe = q_emb if q_emb is not None else (q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs))
+            qe = qe.to(self.device).float()
+        else:
+            qe = None
+        w = self.mixture.field_weights(qe, None, batch=Q)                      # [Q,F] unmasked softmax weights
+        M = len(masked_sets)
+        masks = torch.ones((M, self.num_fields), dtype=torch.float32, device=self.device)
+        for m, idx in enumerate(masked_sets):
+            masks[m, list(idx)] = 0
+        sp, code = self._check_sparse(sparse, Q)
+        out_s = torch.empty((M, Q, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((M, Q, k), dtype=torch.int64, device=self.device)
+        per_chunk = max(1, max_rows // Q)
+        for m0 in range(0, M, per_chunk):
+            m1 = min(M, m0 + per_chunk)
+            reps = m1 - m0
+            w_rows = (w.unsqueeze(0) * masks[m0:m1].unsqueeze(1)).reshape(reps * Q, -1).contiguous()
+            q_rows = q_bf16.repeat(reps, 1) if q_bf16 is not None else None
+            sp_rows = sp.repeat(reps, 1, 1) if sp is not None else None
+            s, i, _ = self._score_topk(q_rows, w_rows, sp_rows, code, k, 0, self.n_dense, self.n_sparse)
+            out_s[m0:m1] = s.view(reps, Q, k)
+            out_i[m0:m1] = i.view(reps, Q, k)
+        return out_s, out_i
+
     # ------------------------------------------------------------------ host-buffer end-to-end call
     def search_host(self, q_vecs_host: torch.Tensor, q_emb_host: Optional[torch.Tensor] = None,
                     sparse_host: Optional[torch.Tensor] = None, top_k: Optional[int] = None,

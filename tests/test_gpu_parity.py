@@ -411,6 +411,30 @@ def test_sparse_coo_input_equals_dense_input_and_oracle(impl, tmp_path):
         assert_topk_parity(s_sh.cpu().numpy(), i_sh.cpu().numpy(), ref[:, lo:hi].numpy(), k, id_offset=lo)
 
 
+def test_mask_sweep_in_one_pass_equals_mask_field_loop():
+    """mask_fields.py:142-170 (baseline, each field, all sparse, all dense, each name) as extra weight rows of one
+    fused pass vs. the reference's procedure: mask_field(idx) + a full search per masking; also vs the oracle."""
+    from mfar_b200.data.schema import resolve_fields
+    finfo = resolve_fields("all_dense,all_sparse", "mag")                      # 5 dense + 5 sparse
+    plan = _mods()[0].mask_sweep_plan(finfo)
+    assert [p[0] for p in plan][:2] == ["baseline", f"field:{next(iter(finfo))}"] and len(plan) == 1 + 10 + 2 + 5
+    Fd = Fs = 5
+    fields, q, sp, W = synth(51, 3000, 768, Fd, Fs, 9, True)
+    r = build(fields, W, True, Fs, 100)
+    S, I = r.search_mask_sweep(q.to(DEV), [p[1] for p in plan], q.to(DEV), sp.to(DEV), max_rows=64)
+    w = O.mixture_weights(q, W, True)
+    for m, (label, idx) in enumerate(plan):
+        r.mask_field(idx)
+        s1, i1 = r.search(q.to(DEV), q.to(DEV), sp.to(DEV))
+        torch.testing.assert_close(S[m], s1, rtol=2e-5, atol=1e-4)
+        assert (I[m] == i1).float().mean().item() > 0.99, label
+        mask = torch.ones(Fd + Fs, 1)
+        mask[idx] = 0
+        ref = O.exhaustive_scores(q, fields, sp.float(), w, mask)
+        assert_topk_parity(S[m].cpu().numpy(), I[m].cpu().numpy(), ref.numpy(), 100)
+    r.mask_field([])
+
+
 def test_peer_exchange_merge_virtual_ranks():
     """The fused NVLink exchange+merge kernel with R "virtual ranks" on one device: R exchange buffers, R concurrent
     streams, each rank pushing into all buffers and spinning on its own flags.  Three epochs (both parities and a
