@@ -169,23 +169,26 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     {                                               // whole warp walks the loop, one elected lane issues
       int stage = 0; uint32_t phase = 0;
       // Query groups (CTA pairs / CTAs with the same blockIdx.y) stream the SAME doc tiles.  They are kept within
-      // one half-tile of each other through per-group progress counters so that the second reader of a tile
+      // one sync interval (a half-tile of >= 8 fields) of each other through per-group progress counters so that the second reader of a tile
       // hits L2 instead of HBM (ncu before: DRAM read 1.8x the corpus at Q=512).  Bounded spin: a group that is
       // not co-resident (SMs taken by another kernel) only costs lockstep, never a deadlock.
       const int n_groups = gridDim.x / CG;
       const int my_group = blockIdx.x / CG;
       int* prog = p.ws.progress + g * n_groups;
       bool lockstep = n_groups > 1 && leader && (G * n_groups <= kProgressInts);
+      // a sync point every ~8 MMA units (= every half-tile when n_dense >= 8): the global round trip must not sit
+      // in front of every TMA issue of a few-field scorer
+      const int sync_every = p.n_dense >= 8 ? 1 : (8 + p.n_dense - 1) / p.n_dense;
       for (int i = 0; i < my_tiles; ++i) {
         const int t = g + i * G;
         for (int h = 0; h < 2; ++h) {
-          if (lockstep) {
+          if (lockstep && ((2 * i + h) % sync_every) == 0) {
             if (lane == 0) {
-              const int idx = 2 * i + h;
-              st_release_gpu(prog + my_group, idx + 1);             // "I am loading half-tile idx"
+              const int idx = (2 * i + h) / sync_every;               // sync point number
+              st_release_gpu(prog + my_group, idx + 1);             // "I am past sync point idx"
               const unsigned long long t0 = clock64();
               for (int o = 0; o < n_groups && lockstep; ++o) {
-                while (ld_acquire_gpu(prog + o) < idx) {            // o has not reached half-tile idx - 1 yet
+                while (ld_acquire_gpu(prog + o) < idx) {            // o has not reached sync point idx - 1 yet
                   if (clock64() - t0 > 200000ull) { lockstep = false; break; }   // ~100 us: give up for good
                   __nanosleep(200);
                 }
@@ -280,6 +283,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     uint64_t thr = 0ull;
     int cnt = 0;
     bool published = false, pool_adopted = false;
+    const int refresh_mask = p.n_dense >= 8 ? 0 : (p.n_dense >= 4 ? 1 : (p.n_dense >= 2 ? 3 : 7));
     float acc[kQsDocs];
     int u = 0;
 #ifdef MFAR_QS_TIMING
@@ -319,7 +323,9 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         }
         // ---- 64 docs scored under every field: + pre-mixed sparse term, threshold filter, push
         const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
-        if (q_valid) {                                 // adopt the best threshold any CTA found for this query
+        // adopt the best threshold any CTA found for this query - an L2 round trip, so not more often than once
+        // per ~8 MMA units (every half-tile when n_dense >= 8, every 8th for a single_ scorer)
+        if (q_valid && (((2 * i + h) & refresh_mask) == 0)) {
           const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + qrow);
           thr = gt > thr ? gt : thr;
           if (!pool_adopted && ld_relaxed_s32(p.ws.gpub + qrow) == G) {   // every CTA of this query has published
