@@ -154,3 +154,58 @@ def test_qres_line_format():
     line = str(QRes("q1", "d9", 0.5))
     assert line == "q1\t0\td9\t0\t0.5\t0"
     assert QRes.from_str(line).doc_id == "d9"
+
+
+def test_precomputed_sparse_scores_loader_matches_reference_dict_semantics(tmp_path):
+    """{field}_keys_bm25.npy int32 [nnz,2] + {field}_vals_bm25.npy f16 [nnz] (precompute_bm25s_scores.py:21-30):
+    lookups behave like the reference's nested dicts (modeling/util.py:112-173, index.py:120-125: missing -> 0),
+    and batch() emits (row-in-batch, doc) pairs grouped by field."""
+    from mfar_b200.data.typedef import Field, FieldType
+    from mfar_b200.modeling.util import PrecomputedSparseScores
+    rng = np.random.RandomState(0)
+    finfo = {"a_dense": Field("a_dense", "a", FieldType.DENSE), "a_sparse": Field("a_sparse", "a", FieldType.SPARSE),
+             "b_sparse": Field("b_sparse", "b", FieldType.SPARSE)}
+    ref = {}
+    for fk in ("a_sparse", "b_sparse"):
+        qids = rng.randint(0, 20, size=300)
+        docs = rng.randint(0, 1000, size=300)
+        pairs = np.unique(np.stack([qids, docs], axis=1), axis=0)
+        pairs = pairs[rng.permutation(len(pairs))].astype(np.int32)
+        vals = rng.gamma(2.0, 2.0, size=len(pairs)).astype(np.float16)
+        np.save(tmp_path / f"{fk}_keys_bm25.npy", pairs)
+        np.save(tmp_path / f"{fk}_vals_bm25.npy", vals)
+        d = {}
+        for (qi, di), v in zip(pairs.tolist(), vals.tolist()):          # the reference's {qid: {doc: score}}
+            d.setdefault(qi, {})[di] = v
+        ref[fk] = d
+    store = PrecomputedSparseScores.load(str(tmp_path), finfo)
+    assert store.field_keys == ["a_sparse", "b_sparse"]
+    for fk in store.field_keys:
+        for qid in (0, 3, 19, 25):
+            for doc in (0, 5, 999) + tuple(ref[fk].get(qid, {}).keys())[:3]:
+                assert store.lookup(fk, qid, doc) == ref[fk].get(qid, {}).get(doc, 0)
+    batch_q = [7, 25, 3]
+    keys, vals, offs = store.batch(batch_q, device="cpu")
+    assert keys.dtype == torch.int32 and keys.shape[1] == 2 and len(offs) == 3 and offs[0] == 0 and offs[-1] == len(vals)
+    for j, fk in enumerate(store.field_keys):
+        seg_k, seg_v = keys[offs[j]:offs[j + 1]].numpy(), vals[offs[j]:offs[j + 1]].numpy()
+        want = {(row, doc): v for row, qid in enumerate(batch_q) for doc, v in ref[fk].get(qid, {}).items()}
+        got = {(int(r), int(d)): float(v) for (r, d), v in zip(seg_k, seg_v)}
+        assert got == {k_: float(np.float16(v)) for k_, v in want.items()}
+
+
+def test_mask_sweep_plan_follows_mask_fields_command():
+    """mfar/commands/mask_fields.py:142-170: baseline, each field, all sparse, all dense, each field name."""
+    from mfar_b200.data.schema import resolve_fields
+    from mfar_b200.modeling.retrieval import MultiFieldRetriever
+    finfo = resolve_fields("all_dense,all_sparse", "amazon")
+    F = len(finfo)
+    plan = MultiFieldRetriever.mask_sweep_plan(finfo)
+    names = sorted({f.name for f in finfo.values()})
+    assert len(plan) == 1 + F + 2 + len(names)
+    assert plan[0] == ("baseline", [])
+    assert [p[1] for p in plan[1:1 + F]] == [[i] for i in range(F)]
+    assert plan[1 + F] == ("all_sparse", list(range(F // 2, F))) and plan[2 + F] == ("all_dense", list(range(F // 2)))
+    for (label, idx), name in zip(plan[3 + F:], names):
+        assert label == f"name:{name}" and len(idx) == 2            # one dense + one sparse column per name
+    assert len(MultiFieldRetriever.mask_sweep_plan(resolve_fields("all_dense", "mag"))) == 1 + 5 + 1 + 5
