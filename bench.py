@@ -198,6 +198,9 @@ def main():
     ap.add_argument("--docs", type=int, default=0, help="override the workload's doc count (debug)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_qs"])
     ap.add_argument("--extra-batches", default="1,64", help="also measured on the device-resident path at N=1")
+    ap.add_argument("--sparse-mode", default="precomputed", choices=["precomputed", "bm25"],
+                    help="sparse fields as precomputed [Q,Fs,N] f16 score tensors (north_star (2)) or scored on the "
+                         "device from query tokens against HBM-resident BM25 postings (SURVEY 8f-3)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
@@ -215,6 +218,10 @@ def main():
                           f"exhaustive hybrid top-{TOPK}, query-conditioned mixture",
               "n_docs": n_total, "n_dense": n_dense, "n_sparse": n_sparse, "dim": DIM, "batch": Q, "top_k": TOPK,
               "sharding": f"doc-range x{world}", "cache": "corpus shard >> 126 MB L2 (inputs larger than L2)"}
+    bm25_mode = args.sparse_mode == "bm25" and n_sparse > 0
+    if n_sparse:
+        config["sparse_input"] = ("device BM25: query tokens -> postings scatter-add (mfar_score_topk_bm25)" if bm25_mode
+                                  else "precomputed [Q,Fs,N] f16 score tensor")
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
@@ -251,7 +258,13 @@ def main():
     layer = LinearWeights(DIM, F, query_cond=True)
     with torch.no_grad():
         layer.weight.copy_(synth.make_mixture(DIM, F, args.seed + 1))
-    retr = MultiFieldRetriever(pc, layer.to(device), n_sparse=n_sparse, top_k=TOPK, doc_id_base=lo, impl=args.kernel)
+    bm25_fields = None
+    if bm25_mode:
+        bm25_fields = [synth.make_bm25_field(n_total, args.seed + 300 + j, device, doc_range=(lo, hi))
+                       for j in range(n_sparse)]
+        torch.cuda.synchronize()
+    retr = MultiFieldRetriever(pc, layer.to(device), n_sparse=n_sparse, top_k=TOPK, doc_id_base=lo, impl=args.kernel,
+                               sparse_indices=bm25_fields)
     exchange, exchange_kind = None, "none (1 GPU)"
     if world > 1:
         from mfar_b200.dist import PeerExchange
@@ -270,9 +283,21 @@ def main():
         pool = []
         for i in range(n_pool):
             qv = synth.make_queries(q_count, DIM, mu, args.seed + 100 + i, device)
-            sp = synth.make_sparse(q_count, n_sparse, hi - lo, args.seed + 200 + i, device, pitch=8)
-            pool.append((qv, qv.float(), sp))
+            if bm25_mode:
+                sp, ent = None, synth.make_bm25_query_entries(q_count, n_sparse, args.seed + 200 + i).to(device)
+            else:
+                sp, ent = synth.make_sparse(q_count, n_sparse, hi - lo, args.seed + 200 + i, device, pitch=8), None
+            pool.append((qv, qv.float(), sp, ent))
         return pool
+
+    def batch_postings(ent):
+        """postings the batch touches on this shard (for the algorithmic byte count)"""
+        total = 0
+        for j, f in enumerate(bm25_fields):
+            t = ent[ent[:, 1] == j][:, 2].long()
+            ip = f.scores["indptr"]
+            total += int((ip[t + 1] - ip[t]).sum().item())
+        return total
 
     def barrier():
         if world > 1:
@@ -281,8 +306,8 @@ def main():
 
     def run_device(pool, steps, warmup, profile=False):
         for i in range(warmup):
-            qv, qe, sp = pool[i % len(pool)]
-            sharded.search(qv, qe, sp)
+            qv, qe, sp, ent = pool[i % len(pool)]
+            sharded.search(qv, qe, sp, sparse_tokens=ent)
         barrier()
         if profile:
             nv.check(nv.lib().mfar_profile_enable(1))
@@ -293,8 +318,8 @@ def main():
             torch.cuda.profiler.start()
         e0.record()
         for i in range(steps):
-            qv, qe, sp = pool[i % len(pool)]
-            sharded.search(qv, qe, sp)
+            qv, qe, sp, ent = pool[i % len(pool)]
+            sharded.search(qv, qe, sp, sparse_tokens=ent)
             launches += retr.last_launches + 1 + 1          # + mixture-weights kernel + cross-shard merge kernel
         e1.record()
         barrier()
@@ -319,8 +344,11 @@ def main():
         out_i = torch.empty((Q, TOPK), dtype=torch.int64).pin_memory()
 
         def one(i):
-            qh, qeh, sph = pool_host[i % len(pool_host)]
-            retr.search_host(qh, qeh, sph, out_scores=out_s, out_ids=out_i)
+            qh, qeh, sph, enth = pool_host[i % len(pool_host)]
+            if bm25_mode:
+                retr.search_host_bm25(qh, qeh, enth, out_scores=out_s, out_ids=out_i)
+            else:
+                retr.search_host(qh, qeh, sph, out_scores=out_s, out_ids=out_i)
         for i in range(warmup):
             one(i)
         barrier()
@@ -342,8 +370,9 @@ def main():
 
     # e2e: N=1 goes through mfar_search_host; N>1 adds the (device) key exchange + merge per step
     pool_host = [(qv.cpu().pin_memory(), qe.cpu().pin_memory(),
-                  None if sp is None else sp[:, :, :hi - lo].contiguous().cpu().pin_memory())   # host call: pitch = N
-                 for qv, qe, sp in pool_dev]
+                  None if sp is None else sp[:, :, :hi - lo].contiguous().cpu().pin_memory(),   # host call: pitch = N
+                  None if ent is None else ent.cpu().pin_memory())
+                 for qv, qe, sp, ent in pool_dev]
     if world == 1:
         ms_e2e = run_e2e(pool_host, args.steps, args.warmup)
     else:
@@ -362,19 +391,32 @@ def main():
             return t.item()
 
         def one_e2e(i):
-            qh, qeh, sph = pool_host[i % len(pool_host)]
+            qh, qeh, sph, enth = pool_host[i % len(pool_host)]
             qv = qh.to(device, non_blocking=True)
             qe = qeh.to(device, non_blocking=True)
             sp = None if sph is None else sph.to(device, non_blocking=True)
-            s, ids = sharded.search(qv, qe, sp)
+            ent = None if enth is None else enth.to(device, non_blocking=True)
+            s, ids = sharded.search(qv, qe, sp, sparse_tokens=ent)
             s.cpu(); ids.cpu()
         ms_e2e = e2e_multi()
-    h2d = Q * DIM * 2 + Q * DIM * 4 + (Q * n_sparse * (hi - lo) * 2 if n_sparse else 0)
+    if bm25_mode:
+        h2d = Q * DIM * 2 + Q * DIM * 4 + pool_dev[0][3].shape[0] * 12
+    else:
+        h2d = Q * DIM * 2 + Q * DIM * 4 + (Q * n_sparse * (hi - lo) * 2 if n_sparse else 0)
     d2h = Q * TOPK * 12
 
     # roofline of the dominant kernel (the fused scoring kernel), per launch, this rank's shard
     n_shard = hi - lo
-    a_bytes, a_flops = algorithmic_work(n_shard, n_dense, n_sparse, Q)
+    a_bytes, a_flops = algorithmic_work(n_shard, n_dense, 0 if bm25_mode else n_sparse, Q)
+    sparse_stage = None
+    if bm25_mode:
+        # per batch: 8 B read per posting touched + the fp32 base[Q,N] row block zeroed, accumulated (L2 atomics) and
+        # read back once by the scoring epilogue
+        postings = statistics.mean(batch_postings(b[3]) for b in pool_dev)
+        sparse_bytes = postings * 8 + 2 * Q * n_shard * 4
+        a_bytes += sparse_bytes
+        sparse_stage = {"postings_per_batch": postings, "algorithmic_bytes": sparse_bytes,
+                        "entries_per_batch": int(pool_dev[0][3].shape[0])}
     k_ms = statistics.mean(kern_ms) if kern_ms else None
     hbm_bound = Q < 200
     if k_ms:
@@ -410,7 +452,7 @@ def main():
             pool = make_batches(qb, 2)
             ms_b, _, km = run_device(pool, max(5, args.steps // 2), 3, profile=True)
             steps_b = max(5, args.steps // 2)
-            bb, ff = algorithmic_work(n_shard, n_dense, n_sparse, qb)
+            bb, ff = algorithmic_work(n_shard, n_dense, 0 if bm25_mode else n_sparse, qb)
             kk = statistics.mean(km) if km else None
             extra.append({"batch": qb, "value": qb * steps_b / (ms_b * 1e-3), "ms_per_step": ms_b / steps_b,
                           "kernel_ms": kk,
@@ -433,7 +475,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "path": "mfar_search_host (C ABI, pinned host buffers)" if world == 1 else
                             "pinned host -> device copies + sharded search + D2H of the merged top-k"},
-            "gpu_launches": launches, "exchange": exchange_kind, "clocks": clocks, "other_batches": extra, "setup_s": setup_s,
+            "sparse_stage": sparse_stage, "gpu_launches": launches, "exchange": exchange_kind, "clocks": clocks, "other_batches": extra, "setup_s": setup_s,
             "kernel_impl": args.kernel,
         }
         print(json.dumps(line))

@@ -146,6 +146,50 @@ MFAR_API int mfar_score_topk_coo(const void* corpus, int64_t n_docs, int corpus_
                         int64_t doc_id_base, int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids,
                         void* workspace, size_t workspace_bytes, int impl, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * BM25 sparse fields scored on the device.  Replaces bm25s.BM25.get_scores as the reference calls it
+ * (BM25sSparseIndex.get_scores / score_batch / retrieve_batch, mfar/data/index.py:72-76, 95-118) and the
+ * score-matrix arithmetic of bm25s.BM25.index (BM25sSparseIndex.create, index.py:134-145; method "lucene",
+ * k1 = 1.2, b = 0.75).  bm25s (0.1.10) is a third-party dependency of the reference: BM25 parity is unpinned
+ * (oracle/bm25_oracle.py restates its published algorithm).
+ *
+ * Per sparse field the index is the token-major (CSC) postings matrix bm25s builds and saves:
+ *   indptr int64 [V+1], indices int32 [nnz] (LOCAL doc rows of this shard, ascending per token), data fp32 [nnz].
+ * The *_host arguments below are HOST arrays of n_sparse DEVICE pointers (one per field).
+ * A query batch is `entries`: DEVICE int32 [n_entries, 3] = (query row, sparse field j, token id), one entry per
+ * query-token occurrence (repeats add up, as in bm25s); entries with an out-of-range member are skipped (a token
+ * that is not in the vocabulary contributes nothing, index.py:112-117 / bm25s get_tokens_ids).
+ * ------------------------------------------------------------------------------------------ */
+/* data[p] = float32( float64(float32(ln(1 + (N - df + 0.5)/(df + 0.5)))) * tf / (k1*(1 - b + b*len/l_avg) + tf) )
+ * for posting p = (post_token[p], post_doc[p], post_tf[p]); df int32 [V], doc_len int32 [n_docs_total]. */
+MFAR_API int mfar_bm25_build_scores(const int32_t* post_token, const int32_t* post_doc, const int32_t* post_tf,
+                                    int64_t nnz, const int32_t* df, const int32_t* doc_len, int64_t n_docs_total,
+                                    double l_avg, double k1, double b, float* data, void* stream);
+
+/* Device scratch the BM25 entry points need for a batch of n_entries query tokens. */
+MFAR_API size_t mfar_bm25_plan_bytes(int64_t n_entries);
+
+/* out[q, doc] (+)= w[q, w_off + j] * score_j(q, doc) over every entry; w == NULL means weight 1.
+ * zero_first != 0 clears out[Q, ld] first: with n_sparse = 1 and w = NULL this is get_scores for a batch
+ * (index.py:72-76) written as fp32 [Q, ld]. */
+MFAR_API int mfar_bm25_scores(const void* const* indptr_host, const void* const* indices_host,
+                              const void* const* data_host, const int32_t* vocab_host, int n_sparse,
+                              const int32_t* entries, int64_t n_entries, int Q, const float* w, int w_ld, int w_off,
+                              int64_t n_docs, float* out, int64_t ld, int zero_first, void* plan, size_t plan_bytes,
+                              void* stream);
+
+/* mfar_score_topk with the sparse fields given as BM25 postings + query tokens instead of score tensors:
+ * workspace must hold mfar_score_topk_bm25_workspace_bytes(...). */
+MFAR_API size_t mfar_score_topk_bm25_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse, int64_t n_entries);
+
+MFAR_API int mfar_score_topk_bm25(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense,
+                                  int dim, const void* q_vecs, int Q, const float* w,
+                                  const void* const* indptr_host, const void* const* indices_host,
+                                  const void* const* data_host, const int32_t* vocab_host, int n_sparse,
+                                  const int32_t* entries, int64_t n_entries, int64_t doc_id_base, int k,
+                                  uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* workspace,
+                                  size_t workspace_bytes, int impl, void* stream);
+
 /* Merge L sorted-or-unsorted key lists per query into the global top-k.  Used for (a) the
  * per-CTA partial lists inside mfar_score_topk and (b) the per-shard lists after the NCCL
  * all-gather (replaces the {rank}.qres file merge of mfar/modeling/contrastive.py:616-631).
@@ -197,6 +241,20 @@ MFAR_API int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fie
                      const float* mask, int query_cond, const void* sparse_host, int n_sparse,
                      int sparse_dtype, int64_t doc_id_base, int k, float* out_scores_host,
                      int64_t* out_ids_host, void* scratch, size_t scratch_bytes, int impl, void* stream);
+
+/* Host-buffer call for hybrid retrieval with device-resident BM25 indices: per batch only the query vectors,
+ * the query embedding and the token entries (HOST int32 [n_entries,3]) cross PCIe - not a [Q,F_s,N] score tensor. */
+MFAR_API size_t mfar_search_host_bm25_scratch_bytes(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
+                                                    int64_t n_entries, int k);
+
+MFAR_API int mfar_search_host_bm25(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin,
+                                   int n_dense, int dim, const void* q_vecs_host, const float* q_emb_host, int Q,
+                                   int E, const float* W, const float* mask, int query_cond,
+                                   const void* const* indptr_host, const void* const* indices_host,
+                                   const void* const* data_host, const int32_t* vocab_host, int n_sparse,
+                                   const int32_t* entries_host, int64_t n_entries, int64_t doc_id_base, int k,
+                                   float* out_scores_host, int64_t* out_ids_host, void* scratch,
+                                   size_t scratch_bytes, int impl, void* stream);
 
 /* Number of kernels the last mfar_score_topk call on this thread launched (bench bookkeeping). */
 MFAR_API int mfar_last_launch_count(void);

@@ -153,11 +153,31 @@ size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_spars
 
 // precomputed per-field sparse scores: dense [Q,Fs,ld] or COO (query row, global doc row, value) grouped by field
 struct SparseInput {
-  int kind = 0;                       // 0 none, 1 dense, 2 COO
+  int kind = 0;                       // 0 none, 1 dense, 2 COO, 3 BM25 postings + query tokens
   const void* dense = nullptr; int dense_dtype = MFAR_F16; int64_t dense_ld = 0;
   const int32_t* coo_keys = nullptr; const void* coo_vals = nullptr; int coo_dtype = MFAR_F16;
   const int64_t* field_offsets_host = nullptr;
+  Bm25Fields bm25{}; const int32_t* entries = nullptr; int64_t n_entries = 0;   // kind 3
 };
+
+static size_t bm25_plan_bytes(int64_t n_entries) {
+  // ent_first [n] + flat_start [n+1], int64
+  return align_up(size_t(2 * std::max<int64_t>(n_entries, 0) + 1) * 8, 256);
+}
+
+static int fill_bm25_fields(const void* const* indptr_host, const void* const* indices_host,
+                            const void* const* data_host, const int32_t* vocab_host, int n_sparse, Bm25Fields* f) {
+  if (!indptr_host || !indices_host || !data_host || !vocab_host) return MFAR_ERR_ARG;
+  if (n_sparse <= 0 || n_sparse > MFAR_MAX_FIELDS) return MFAR_ERR_SHAPE;
+  for (int j = 0; j < n_sparse; ++j) {
+    if (!indptr_host[j] || vocab_host[j] < 0) return MFAR_ERR_ARG;
+    f->indptr[j] = static_cast<const long long*>(indptr_host[j]);
+    f->indices[j] = static_cast<const int*>(indices_host[j]);     // may be null for an empty field (nnz == 0)
+    f->data[j] = static_cast<const float*>(data_host[j]);
+    f->vocab[j] = vocab_host[j];
+  }
+  return MFAR_OK;
+}
 
 static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
                            const void* q_vecs, int Q, const float* w, const SparseInput& sp, int n_sparse,
@@ -172,6 +192,7 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   if (n_sparse > 0 && sp.kind == 1 && (!sp.dense || sp.dense_ld < n_docs)) return MFAR_ERR_ARG;
   if (n_sparse > 0 && sp.kind == 2 && (!sp.field_offsets_host || sp.field_offsets_host[0] != 0)) return MFAR_ERR_ARG;
   if (n_sparse > 0 && sp.kind == 0) return MFAR_ERR_ARG;
+  if (n_sparse > 0 && sp.kind == 3 && (sp.n_entries < 0 || (sp.n_entries > 0 && !sp.entries))) return MFAR_ERR_ARG;
   if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
   if (doc_id_base < 0 || doc_id_base + n_docs > (int64_t(1) << 32)) return MFAR_ERR_SHAPE;
   if (impl < MFAR_IMPL_AUTO || impl > MFAR_IMPL_TCGEN05_QS) return MFAR_ERR_ARG;
@@ -189,7 +210,8 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   const size_t ws_topk = align_up(topk_workspace_bytes(g.workers, g.q_pad_total), 256);
   const int64_t base_ld = int64_t(align_up(size_t(n_docs), kTileDocs));   // tile-wide vector reads stay in bounds
   const size_t ws_base = n_sparse > 0 ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
-  if (workspace_bytes < ws_topk + ws_base) return MFAR_ERR_WORKSPACE;
+  const size_t ws_plan = (n_sparse > 0 && sp.kind == 3) ? bm25_plan_bytes(sp.n_entries) : 0;
+  if (workspace_bytes < ws_topk + ws_base + ws_plan) return MFAR_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MFAR_ERR_ARG;
 
   if (n_sparse > 0) {
@@ -199,6 +221,19 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
                                         base, base_ld, st))
         return rc;
       ++t_last_launches;
+    } else if (sp.kind == 3) {
+      MFAR_CUDA_OK(cudaMemsetAsync(base, 0, size_t(Q) * base_ld * 4, st));
+      ++t_last_launches;
+      if (sp.n_entries > 0) {
+        long long* ent_first = reinterpret_cast<long long*>(static_cast<char*>(workspace) + ws_topk + ws_base);
+        long long* flat_start = ent_first + sp.n_entries;
+        if (int rc = launch_bm25_plan(sp.entries, sp.n_entries, sp.bm25, n_sparse, Q, ent_first, flat_start, st))
+          return rc;
+        if (int rc = launch_bm25_scatter(sp.entries, sp.n_entries, ent_first, flat_start, sp.bm25, w, a.w_ld, n_dense,
+                                         n_docs, base, base_ld, st))
+          return rc;
+        t_last_launches += 2;
+      }
     } else {
       MFAR_CUDA_OK(cudaMemsetAsync(base, 0, size_t(Q) * base_ld * 4, st));
       if (int rc = launch_sparse_premix_coo(sp.coo_keys, sp.coo_vals, sp.coo_dtype, sp.field_offsets_host, n_sparse, w,
@@ -250,6 +285,60 @@ int mfar_score_topk_coo(const void* corpus, int64_t n_docs, int corpus_fields, i
   SparseInput sp;
   sp.kind = 2; sp.coo_keys = coo_keys; sp.coo_vals = coo_vals; sp.coo_dtype = coo_dtype;
   sp.field_offsets_host = field_offsets_host;
+  return score_topk_core(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, q_vecs, Q, w, sp, n_sparse,
+                         doc_id_base, k, out_keys, out_scores, out_ids, workspace, workspace_bytes, impl, stream);
+}
+
+int mfar_bm25_build_scores(const int32_t* post_token, const int32_t* post_doc, const int32_t* post_tf, int64_t nnz,
+                           const int32_t* df, const int32_t* doc_len, int64_t n_docs_total, double l_avg, double k1,
+                           double b, float* data, void* stream) {
+  if (nnz < 0 || n_docs_total <= 0 || !(l_avg > 0.0)) return MFAR_ERR_ARG;
+  if (nnz > 0 && (!post_token || !post_doc || !post_tf || !df || !doc_len || !data)) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  return launch_bm25_build_scores(post_token, post_doc, post_tf, nnz, df, doc_len, n_docs_total, l_avg, k1, b, data,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+size_t mfar_bm25_plan_bytes(int64_t n_entries) { return bm25_plan_bytes(n_entries); }
+
+int mfar_bm25_scores(const void* const* indptr_host, const void* const* indices_host, const void* const* data_host,
+                     const int32_t* vocab_host, int n_sparse, const int32_t* entries, int64_t n_entries, int Q,
+                     const float* w, int w_ld, int w_off, int64_t n_docs, float* out, int64_t ld, int zero_first,
+                     void* plan, size_t plan_bytes, void* stream) {
+  t_last_launches = 0;
+  if (!out || Q <= 0 || n_docs <= 0 || ld < n_docs || n_entries < 0 || (n_entries > 0 && (!entries || !plan)))
+    return MFAR_ERR_ARG;
+  if (w && (w_ld <= 0 || w_off < 0 || w_off + n_sparse > w_ld)) return MFAR_ERR_ARG;
+  if (plan_bytes < bm25_plan_bytes(n_entries)) return MFAR_ERR_WORKSPACE;
+  Bm25Fields f{};
+  if (int rc = fill_bm25_fields(indptr_host, indices_host, data_host, vocab_host, n_sparse, &f)) return rc;
+  if (int rc = check_arch()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (zero_first) { MFAR_CUDA_OK(cudaMemsetAsync(out, 0, size_t(Q) * ld * 4, st)); ++t_last_launches; }
+  if (n_entries == 0) return MFAR_OK;
+  long long* ent_first = static_cast<long long*>(plan);
+  long long* flat_start = ent_first + n_entries;
+  if (int rc = launch_bm25_plan(entries, n_entries, f, n_sparse, Q, ent_first, flat_start, st)) return rc;
+  if (int rc = launch_bm25_scatter(entries, n_entries, ent_first, flat_start, f, w, w_ld, w_off, n_docs, out, ld, st))
+    return rc;
+  t_last_launches += 2;
+  return MFAR_OK;
+}
+
+size_t mfar_score_topk_bm25_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse, int64_t n_entries) {
+  const size_t b = mfar_score_topk_workspace_bytes(Q, k, n_docs, n_sparse);
+  return b ? b + bm25_plan_bytes(n_entries) : 0;
+}
+
+int mfar_score_topk_bm25(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
+                         const void* q_vecs, int Q, const float* w, const void* const* indptr_host,
+                         const void* const* indices_host, const void* const* data_host, const int32_t* vocab_host,
+                         int n_sparse, const int32_t* entries, int64_t n_entries, int64_t doc_id_base, int k,
+                         uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* workspace,
+                         size_t workspace_bytes, int impl, void* stream) {
+  SparseInput sp;
+  sp.kind = 3; sp.entries = entries; sp.n_entries = n_entries;
+  if (int rc = fill_bm25_fields(indptr_host, indices_host, data_host, vocab_host, n_sparse, &sp.bm25)) return rc;
   return score_topk_core(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, q_vecs, Q, w, sp, n_sparse,
                          doc_id_base, k, out_keys, out_scores, out_ids, workspace, workspace_bytes, impl, stream);
 }
@@ -357,6 +446,72 @@ int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int 
   int rc = mfar_score_topk(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, s + h.off_q, Q, w_dev,
                            n_sparse ? s + h.off_sparse : nullptr, n_sparse, sparse_dtype, n_docs, doc_id_base, k,
                            nullptr, sc, ids, s + h.off_ws, h.ws_bytes, impl, st);
+  if (rc) return rc;
+  t_last_launches += 1;
+  MFAR_CUDA_OK(cudaMemcpyAsync(out_scores_host, sc, size_t(Q) * k * 4, cudaMemcpyDeviceToHost, st));
+  MFAR_CUDA_OK(cudaMemcpyAsync(out_ids_host, ids, size_t(Q) * k * 8, cudaMemcpyDeviceToHost, st));
+  MFAR_CUDA_OK(cudaStreamSynchronize(st));
+  return MFAR_OK;
+}
+
+struct HostScratchBm25 { size_t off_q, off_qe, off_w, off_ent, off_scores, off_ids, off_ws, total, ws_bytes; };
+static HostScratchBm25 host_scratch_bm25_layout(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
+                                                int64_t n_entries, int k) {
+  HostScratchBm25 h{};
+  size_t o = 0;
+  h.off_q = o;      o += align_up(size_t(Q) * std::max(dim, 1) * 2, 256);
+  h.off_qe = o;     o += align_up(size_t(Q) * std::max(E, 1) * 4, 256);
+  h.off_w = o;      o += align_up(size_t(Q) * (n_dense + n_sparse) * 4, 256);
+  h.off_ent = o;    o += align_up(size_t(std::max<int64_t>(n_entries, 1)) * 12, 256);
+  h.off_scores = o; o += align_up(size_t(Q) * k * 4, 256);
+  h.off_ids = o;    o += align_up(size_t(Q) * k * 8, 256);
+  h.off_ws = o;
+  h.ws_bytes = mfar_score_topk_bm25_workspace_bytes(Q, k, n_docs, n_sparse, n_entries);
+  h.total = o + h.ws_bytes;
+  return h;
+}
+
+size_t mfar_search_host_bm25_scratch_bytes(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
+                                           int64_t n_entries, int k) {
+  if (Q <= 0 || n_docs <= 0 || n_entries < 0) return 0;
+  return host_scratch_bm25_layout(Q, dim, E, n_dense, n_sparse, n_docs, n_entries, k).total;
+}
+
+int mfar_search_host_bm25(const void* corpus, int64_t n_docs, int corpus_fields, int field_begin, int n_dense, int dim,
+                          const void* q_vecs_host, const float* q_emb_host, int Q, int E, const float* W,
+                          const float* mask, int query_cond, const void* const* indptr_host,
+                          const void* const* indices_host, const void* const* data_host, const int32_t* vocab_host,
+                          int n_sparse, const int32_t* entries_host, int64_t n_entries, int64_t doc_id_base, int k,
+                          float* out_scores_host, int64_t* out_ids_host, void* scratch, size_t scratch_bytes, int impl,
+                          void* stream) {
+  if (!scratch || !W || !out_scores_host || !out_ids_host || Q <= 0 || n_docs <= 0 || n_entries < 0)
+    return MFAR_ERR_ARG;
+  if (n_dense > 0 && !q_vecs_host) return MFAR_ERR_ARG;
+  if (query_cond && !q_emb_host) return MFAR_ERR_ARG;
+  if (n_entries > 0 && !entries_host) return MFAR_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(scratch) % 256 != 0) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  const HostScratchBm25 h = host_scratch_bm25_layout(Q, dim, E, n_dense, n_sparse, n_docs, n_entries, k);
+  if (scratch_bytes < h.total) return MFAR_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* s = static_cast<char*>(scratch);
+  const int F = n_dense + n_sparse;
+  if (n_dense > 0)
+    MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_q, q_vecs_host, size_t(Q) * dim * 2, cudaMemcpyHostToDevice, st));
+  if (query_cond)
+    MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_qe, q_emb_host, size_t(Q) * E * 4, cudaMemcpyHostToDevice, st));
+  if (n_entries > 0)
+    MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_ent, entries_host, size_t(n_entries) * 12, cudaMemcpyHostToDevice, st));
+  float* w_dev = reinterpret_cast<float*>(s + h.off_w);
+  if (int rc = launch_mixture_weights(query_cond ? reinterpret_cast<const float*>(s + h.off_qe) : nullptr, W, mask, Q,
+                                      E, F, query_cond, w_dev, st))
+    return rc;
+  float* sc = reinterpret_cast<float*>(s + h.off_scores);
+  int64_t* ids = reinterpret_cast<int64_t*>(s + h.off_ids);
+  int rc = mfar_score_topk_bm25(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, s + h.off_q, Q, w_dev,
+                                indptr_host, indices_host, data_host, vocab_host, n_sparse,
+                                reinterpret_cast<const int32_t*>(s + h.off_ent), n_entries, doc_id_base, k, nullptr, sc,
+                                ids, s + h.off_ws, h.ws_bytes, impl, st);
   if (rc) return rc;
   t_last_launches += 1;
   MFAR_CUDA_OK(cudaMemcpyAsync(out_scores_host, sc, size_t(Q) * k * 4, cudaMemcpyDeviceToHost, st));

@@ -3,7 +3,25 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mfar_b200.h"
+
 namespace mfar {
+
+// BM25 postings of every sparse field (device pointers), passed to kernels by value.
+struct Bm25Fields {
+  const long long* indptr[MFAR_MAX_FIELDS];   // int64 [V_j + 1]
+  const int* indices[MFAR_MAX_FIELDS];        // int32 [nnz_j] local doc rows
+  const float* data[MFAR_MAX_FIELDS];         // fp32  [nnz_j]
+  int vocab[MFAR_MAX_FIELDS];                 // V_j
+};
+int launch_bm25_plan(const int* entries, long long n_entries, const Bm25Fields& f, int n_sparse, int Q,
+                     long long* ent_first, long long* flat_start, cudaStream_t st);
+int launch_bm25_scatter(const int* entries, long long n_entries, const long long* ent_first,
+                        const long long* flat_start, const Bm25Fields& f, const float* w, int w_ld, int w_off,
+                        long long n_docs, float* base, long long base_ld, cudaStream_t st);
+int launch_bm25_build_scores(const int* post_token, const int* post_doc, const int* post_tf, long long nnz,
+                             const int* df, const int* doc_len, long long n_docs_total, double l_avg, double k1,
+                             double b, float* data, cudaStream_t st);
 
 int launch_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin, void* packed,
                      int n_fields, int field, int dim, int normalize, cudaStream_t st);

@@ -296,8 +296,20 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     for (int i = 0; i < my_tiles; ++i) {
       const int t = g + i * G;
       for (int h = 0; h < 2; ++h) {
+        const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
+        // accumulators start from the pre-mixed sparse term (16 x 16-byte loads per query row, issued ahead of the
+        // wait for the half-tile's first accumulator; base_ld is a multiple of 128, so the row read stays in bounds)
+        if (my_base != nullptr && q_valid && doc0 < p.n_docs) {
+          const float4* b4 = reinterpret_cast<const float4*>(my_base + doc0);
 #pragma unroll
-        for (int c = 0; c < kQsDocs; ++c) acc[c] = 0.f;
+          for (int c = 0; c < kQsDocs; c += 4) {
+            const float4 b = __ldg(b4 + c / 4);
+            acc[c] = b.x; acc[c + 1] = b.y; acc[c + 2] = b.z; acc[c + 3] = b.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kQsDocs; ++c) acc[c] = 0.f;
+        }
         for (int f = 0; f < p.n_dense; ++f, ++u) {
           const int buf = u & 1;
           mbar_wait(&tfull_bar[buf], (u >> 1) & 1, err, 15);
@@ -321,8 +333,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           for (int c = 0; c < kQsDocs; ++c) acc[c] = fmaf(wf, __uint_as_float(v[c]), acc[c]);
           QS_ETICK(e_drain)
         }
-        // ---- 64 docs scored under every field: + pre-mixed sparse term, threshold filter, push
-        const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
+        // ---- 64 docs scored under every field: threshold filter, push
         // adopt the best threshold any CTA found for this query - an L2 round trip, so not more often than once
         // per ~8 MMA units (every half-tile when n_dense >= 8, every 8th for a single_ scorer)
         if (q_valid && (((2 * i + h) & refresh_mask) == 0)) {
@@ -337,14 +348,6 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         if (q_valid && doc0 < p.n_docs) {
           const int64_t left = p.n_docs - doc0;
           const int nd = left < kQsDocs ? int(left) : kQsDocs;
-          if (my_base) {
-            const float4* b4 = reinterpret_cast<const float4*>(my_base + doc0);
-#pragma unroll
-            for (int c = 0; c < kQsDocs; c += 4) {
-              const float4 b = __ldg(b4 + c / 4);
-              acc[c] += b.x; acc[c + 1] += b.y; acc[c + 2] += b.z; acc[c + 3] += b.w;
-            }
-          }
           const uint32_t id0 = uint32_t(p.doc_id_base + doc0);
           // one float compare per doc rejects almost everything; the exact (score, id) key is only built for docs
           // whose score reaches the threshold's score (thr == 0: nothing established yet, admit all)

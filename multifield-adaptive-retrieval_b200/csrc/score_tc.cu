@@ -179,8 +179,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         epi_bar_sync();
       }
+      // The accumulators start from the pre-mixed sparse term: its QP loads per doc (coalesced across the warp's
+      // 32 docs) are issued here, ahead of the wait for the tile's first accumulator, instead of serialising with
+      // the push loop after the last field.
+      const int64_t doc_local = int64_t(t) * kTileDocs + doc_in_tile;
+      if (p.base != nullptr && doc_local < p.n_docs) {
+        const float* bp = p.base + int64_t(q0) * p.base_ld + doc_local;
 #pragma unroll
-      for (int c = 0; c < QP; ++c) acc[c] = 0.f;
+        for (int c = 0; c < QP; ++c) acc[c] = (c < nq) ? __ldg(bp + int64_t(c) * p.base_ld) : 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < QP; ++c) acc[c] = 0.f;
+      }
       for (int f = 0; f < p.n_dense; ++f, ++u) {
         const int buf = u & 1;
         mbar_wait(&tfull_bar[buf], (u >> 1) & 1, err, 5);
@@ -204,16 +214,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         tc_fence_before();
         mbar_arrive(&tempty_bar[buf]);             // 128 arrivals free the accumulator buffer
       }
-      // ---- tile done: add pre-mixed sparse term, filter, push
-      const int64_t doc_local = int64_t(t) * kTileDocs + doc_in_tile;
+      // ---- tile done: filter, push
       if (doc_local < p.n_docs) {
         const uint32_t doc_id = uint32_t(p.doc_id_base + doc_local);
 #pragma unroll
         for (int c = 0; c < QP; ++c) {
           if (c < nq) {
-            float s = acc[c];
-            if (p.base) s += __ldg(p.base + int64_t(q0 + c) * p.base_ld + doc_local);
-            const uint64_t key = make_key(s, doc_id);
+            const uint64_t key = make_key(acc[c], doc_id);
             if (key > s_thr[c]) {
               const int pos = atomicAdd(&s_cnt[c], 1);
               __stcg(p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap + pos, key);

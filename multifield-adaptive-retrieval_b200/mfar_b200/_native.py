@@ -19,7 +19,7 @@ MAX_FIELDS = 64
 
 _lib = None
 
-_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+_vp, _i, _i64, _sz, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
 PROTOTYPES = {
@@ -44,6 +44,15 @@ PROTOTYPES = {
     "mfar_search_host_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i64, _i, _i]),
     "mfar_search_host": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i64, _i,
                               _vp, _vp, _vp, _sz, _i, _vp]),
+    "mfar_bm25_build_scores": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _f64, _f64, _f64, _vp, _vp]),
+    "mfar_bm25_plan_bytes": (_sz, [_i64]),
+    "mfar_bm25_scores": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64, _i, _vp, _i, _i, _i64, _vp, _i64, _i, _vp, _sz, _vp]),
+    "mfar_score_topk_bm25_workspace_bytes": (_sz, [_i, _i, _i64, _i, _i64]),
+    "mfar_score_topk_bm25": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _i64, _i,
+                                  _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "mfar_search_host_bm25_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i64, _i64, _i]),
+    "mfar_search_host_bm25": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i,
+                                   _vp, _i64, _i64, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "mfar_last_launch_count": (_i, []),
     "mfar_profile_enable": (_i, [_i]),
     "mfar_profile_collect": (_i, [_vp, _i]),

@@ -3,10 +3,11 @@
 ``Index``                  - the ABC (index.py:21-37)
 ``DenseFlatIndex``         - exhaustive flat dense index over ONE field (index.py:160-232); same
                              constructor and return types, every dot product / top-k on the GPU
-``PrecomputedSparseIndex`` - stands where ``BM25sSparseIndex`` stands (index.py:39-157) for this
-                             path: BM25 arithmetic (third-party bm25s) is out of scope, the index
-                             serves PRECOMPUTED per-query full-corpus score vectors and does the
-                             gather / top-k the reference does around them (index.py:95-118)
+``BM25sSparseIndex``       - the reference's sparse index (index.py:39-157) over a device-resident
+                             ``DeviceBM25`` (postings in HBM, scatter-add kernel) instead of ``bm25s.BM25``
+``PrecomputedSparseIndex`` - sparse index fed with PRECOMPUTED per-query full-corpus score vectors
+                             (what ``get_scores`` returns); does the gather / top-k the reference does
+                             around them (index.py:95-118)
 """
 from __future__ import annotations
 
@@ -101,6 +102,106 @@ class DenseFlatIndex(Index[str, str]):
         r = self._ensure()
         rows = torch.tensor([self.key_to_numeric_ids[k] for k in keys], dtype=torch.int64)
         return r.score_candidates(self._encode(queries), rows)[0]
+
+
+class BM25sSparseIndex(Index[str, str]):
+    """``BM25sSparseIndex`` (index.py:39-157) with the BM25 score matrix in HBM.
+
+    Same constructor, methods and return types; ``index`` is a ``mfar_b200.data.bm25.DeviceBM25`` (stands where
+    ``bm25s.BM25`` stands).  ``get_scores`` keeps the reference's per-query cache (index.py:71, ``lru_cache``)."""
+
+    def __init__(self, keys: List[str], index, stemmer=None, index_limit: int = 5000, safe_docs=None):
+        self.keys = keys
+        self.key_to_id = {key: i for i, key in enumerate(keys)}
+        self.index = index
+        self.stemmer = stemmer
+        self.index_limit = index_limit
+        self.safe_docs = safe_docs if safe_docs is not None else {}
+        self.name = None
+        self._score_cache: Dict[str, np.ndarray] = {}
+        self._cache_size = 2 ** 15                                   # index.py:71
+
+    def set_safe_docs(self, safe_docs):
+        self.safe_docs = safe_docs
+
+    def tokenize(self, queries, stopwords="en", stemmer=None, return_ids: bool = False):
+        """index.py:55-69 with return_ids=False: token list for a str, list of token lists for a sequence."""
+        from .bm25 import tokenize
+        if isinstance(queries, str):
+            return tokenize(queries, stopwords, stemmer)[0]
+        return tokenize(list(queries), stopwords, stemmer)
+
+    def get_scores(self, query: str) -> np.ndarray:
+        """fp32 [N] BM25 scores of one query against the whole field corpus (index.py:72-76)."""
+        hit = self._score_cache.get(query)
+        if hit is not None:
+            return hit
+        tokens = self.tokenize(query, stopwords="en", stemmer=self.stemmer)
+        score = self.index.get_scores(tokens) if tokens else np.zeros(self.index.num_docs, dtype=np.float32)
+        if len(self._score_cache) >= self._cache_size:
+            self._score_cache.pop(next(iter(self._score_cache)))
+        self._score_cache[query] = score
+        return score
+
+    def get_scores_sparse(self, query: str) -> Dict[int, float]:
+        """index.py:78-84: nonzero scores of the docs in ``safe_docs``."""
+        dense = self.get_scores(query)
+        return {int(i): dense[i] for i in np.nonzero(dense)[0] if int(i) in self.safe_docs}
+
+    def retrieve(self, query: str, top_k: int):
+        return self.retrieve_batch([query], top_k)[0]                # index.py:86-93
+
+    def retrieve_batch(self, queries: Sequence[str], top_k: int):
+        """index.py:95-103: [(key, score)] x top_k per query, best first."""
+        tokens = self.tokenize(list(queries), stopwords="en", stemmer=self.stemmer)
+        rows, scores = self.index.retrieve(tokens, k=top_k)
+        return [[(self.keys[rows[i, j]], scores[i, j]) for j in range(rows.shape[1])] for i in range(rows.shape[0])]
+
+    def score(self, query: str, keys: Sequence[str]) -> np.ndarray:
+        doc_ids = np.array([self.key_to_id[key] for key in keys])    # index.py:105-109 (unknown key: KeyError)
+        return self.get_scores(query)[doc_ids]
+
+    def score_batch(self, queries: Sequence[str], keys: Sequence[str]) -> torch.Tensor:
+        """[Q, C] scores of the given keys; keys missing from the index score 0 (index.py:111-118)."""
+        rows = torch.tensor([self.key_to_id.get(k, -1) for k in keys], dtype=torch.int64, device=self.index.device)
+        tokens = self.tokenize(list(queries), stopwords="en", stemmer=self.stemmer)
+        sv = self.index.get_scores_batch(tokens)                     # [Q, N] on the device
+        out = sv[:, rows.clamp(min=0)]
+        return (out * (rows >= 0).to(out.dtype)).cpu()
+
+    def score_batch_with_cache(self, query_ids: List[int], keys: Sequence[str], sparse_scores: Dict) -> torch.Tensor:
+        """index.py:120-125: lookup in precomputed ``{qid: {doc_id: score}}`` dicts, missing -> 0."""
+        all_doc_scores = [sparse_scores.get(qid, {}) for qid in query_ids]
+        doc_ids = [self.key_to_id[key] for key in keys]
+        return torch.tensor([[s.get(d, 0) for d in doc_ids] for s in all_doc_scores])
+
+    @classmethod
+    def create(cls, corpus, stemmer=None, dataset_name: Optional[str] = "", device="cuda"):
+        """index.py:134-145.  ``corpus``: anything with ``keys()`` and ``docs`` (objects with ``.text``), or a
+        ``{key: text}`` dict."""
+        from .bm25 import DeviceBM25, tokenize
+        if isinstance(corpus, dict):
+            keys, texts = list(corpus.keys()), list(corpus.values())
+        else:
+            keys, texts = list(corpus.keys()), [d.text for d in corpus.docs]
+        index = DeviceBM25(k1=1.2, b=0.75, method="lucene", device=device)
+        index.index(tokenize(texts, stopwords="en", stemmer=stemmer))
+        index_limit = 5000 if dataset_name == "amazon" else 12000
+        return cls(keys, index, stemmer, index_limit)
+
+    def save(self, path: str):
+        import json
+        self.index.save(f"{path}/index")
+        with open(f"{path}/keys.json", "w") as f:
+            json.dump(self.keys, f)
+
+    @classmethod
+    def load(cls, path: str, stemmer=None, device="cuda"):
+        import json
+        from .bm25 import DeviceBM25
+        with open(f"{path}/keys.json", "r") as f:
+            keys = json.load(f)
+        return cls(keys, DeviceBM25.load(f"{path}/index", mmap=True, device=device), stemmer)
 
 
 class PrecomputedSparseIndex(Index[str, str]):

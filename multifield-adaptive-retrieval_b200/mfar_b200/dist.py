@@ -119,10 +119,13 @@ class ShardedRetriever:
         self.exchange = exchange          # None: NCCL/gloo all-gather + merge kernel; else the fused NVLink kernel
 
     @torch.no_grad()
-    def search(self, q_vecs, q_emb=None, sparse_local=None, top_k: Optional[int] = None):
+    def search(self, q_vecs, q_emb=None, sparse_local=None, top_k: Optional[int] = None, sparse_tokens=None):
+        """``sparse_local``: this shard's columns of the precomputed sparse scores; ``sparse_tokens``: the (replicated)
+        query tokens when the local retriever holds this shard's BM25 postings (``DeviceBM25.shard``)."""
         k = top_k or self.local.top_k
         k_local = min(k, self.local.n_docs)
-        _, _, keys = self.local.search(q_vecs, q_emb, sparse_local, top_k=k_local, return_keys=True)
+        _, _, keys = self.local.search(q_vecs, q_emb, sparse_local, top_k=k_local, return_keys=True,
+                                       sparse_tokens=sparse_tokens)
         if k_local < k:                                   # tiny shard: pad with empty keys
             keys = torch.nn.functional.pad(keys, (0, k - k_local))
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:

@@ -117,12 +117,23 @@ class MultiFieldRetriever:
 
     def __init__(self, corpus: Optional[PackedCorpus], mixture: LinearWeights, n_sparse: int = 0, top_k: int = 100,
                  doc_id_base: int = 0, n_docs: Optional[int] = None, impl: str = "auto",
-                 numeric_ids_to_keys: Optional[Sequence[str]] = None, device=None):
+                 numeric_ids_to_keys: Optional[Sequence[str]] = None, device=None, sparse_indices=None):
+        """``sparse_indices``: the shard's ``DeviceBM25`` indices, one per sparse field in field order; with them the
+        sparse fields are scored on the device from query tokens (``sparse_tokens=``) and ``n_sparse`` is implied."""
         self.corpus = corpus
         self.n_dense = corpus.n_fields if corpus is not None else 0
+        self.bm25 = None
+        if sparse_indices is not None and len(sparse_indices):
+            from ..data.bm25 import BM25FieldSet
+            self.bm25 = BM25FieldSet(sparse_indices)
+            n_sparse = len(sparse_indices)
+            if n_docs is None and corpus is None:
+                n_docs = self.bm25.num_docs
         self.n_sparse = int(n_sparse)
         self.n_docs = corpus.n_docs if corpus is not None else int(n_docs)
         self.device = corpus.device if corpus is not None else torch.device(device or "cuda")
+        if self.bm25 is not None and self.bm25.num_docs != self.n_docs:
+            raise ValueError(f"BM25 indices hold {self.bm25.num_docs} docs, the shard {self.n_docs}")
         self.mixture = mixture
         if mixture.num_fields != self.n_dense + self.n_sparse:
             raise ValueError(f"mixture has {mixture.num_fields} fields, retriever {self.n_dense}+{self.n_sparse}")
@@ -149,8 +160,10 @@ class MultiFieldRetriever:
             self.masked_fields_string = ",".join(field_names[i] for i in field_idx_list)
 
     # ------------------------------------------------------------------ internals
-    def _workspace(self, Q: int, k: int, n_sparse: int, n_docs: Optional[int] = None) -> torch.Tensor:
-        need = nv.lib().mfar_score_topk_workspace_bytes(Q, k, self.n_docs if n_docs is None else n_docs, n_sparse)
+    def _workspace(self, Q: int, k: int, n_sparse: int, n_docs: Optional[int] = None,
+                   n_entries: int = 0) -> torch.Tensor:
+        need = nv.lib().mfar_score_topk_bm25_workspace_bytes(Q, k, self.n_docs if n_docs is None else n_docs,
+                                                             n_sparse, n_entries)
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
@@ -169,7 +182,8 @@ class MultiFieldRetriever:
 
     def _score_topk(self, q_bf16: Optional[torch.Tensor], w: torch.Tensor, sparse, sparse_code: int, k: int,
                     field_begin: int, n_dense: int, n_sparse: int, want_keys: bool = False, impl: Optional[str] = None,
-                    n_docs: Optional[int] = None, doc_id_base: Optional[int] = None, sparse_coo=None):
+                    n_docs: Optional[int] = None, doc_id_base: Optional[int] = None, sparse_coo=None,
+                    bm25_entries: Optional[torch.Tensor] = None):
         Q = w.shape[0]
         n_docs = self.n_docs if n_docs is None else n_docs
         doc_id_base = self.doc_id_base if doc_id_base is None else doc_id_base
@@ -178,8 +192,18 @@ class MultiFieldRetriever:
         scores = torch.empty((Q, k), dtype=torch.float32, device=self.device)
         ids = torch.empty((Q, k), dtype=torch.int64, device=self.device)
         keys = torch.empty((Q, k), dtype=torch.int64, device=self.device) if want_keys else None
-        ws = self._workspace(Q, k, n_sparse, n_docs)
+        ws = self._workspace(Q, k, n_sparse, n_docs, 0 if bm25_entries is None else bm25_entries.shape[0])
         c = self.corpus
+        if bm25_entries is not None:
+            b = self.bm25
+            nv.check(nv.lib().mfar_score_topk_bm25(
+                nv.ptr(c.data) if c is not None else 0, n_docs, c.n_fields if c is not None else 0, field_begin,
+                n_dense, c.dim_pad if c is not None else 0, nv.ptr(q_bf16), Q, nv.ptr(w), b.indptr, b.indices, b.data,
+                b.vocab, n_sparse, nv.ptr(bm25_entries), bm25_entries.shape[0], doc_id_base, k, nv.ptr(keys),
+                nv.ptr(scores), nv.ptr(ids), nv.ptr(ws), ws.numel(), nv.IMPL[impl or self.impl], nv.stream()),
+                "score_topk_bm25")
+            self.last_launches = nv.lib().mfar_last_launch_count()
+            return scores, ids, keys
         if sparse_coo is not None:
             import ctypes
             coo_keys, coo_vals, offsets = sparse_coo
@@ -201,10 +225,39 @@ class MultiFieldRetriever:
         self.last_launches = nv.lib().mfar_last_launch_count()
         return scores, ids, keys
 
+    def _bm25_entries(self, sparse_tokens) -> torch.Tensor:
+        if self.bm25 is None:
+            raise ValueError("sparse_tokens needs a retriever built with sparse_indices=[DeviceBM25, ...]")
+        if torch.is_tensor(sparse_tokens):
+            nv.require_device(sparse_tokens, "sparse_tokens")
+            if sparse_tokens.dtype != torch.int32 or sparse_tokens.dim() != 2 or sparse_tokens.shape[1] != 3:
+                raise ValueError("entry tensor must be int32 [n,3] = (query row, sparse field, token id)")
+            return sparse_tokens.contiguous()
+        return self.bm25.entries(sparse_tokens)
+
+    def _sparse_from_tokens(self, sparse, sparse_tokens, q_bf16) -> Optional[torch.Tensor]:
+        """Per-field score tensor [Q,F_s,ld] from query tokens when the sparse fields are BM25 indices."""
+        if sparse_tokens is None:
+            return sparse
+        if q_bf16 is not None:
+            Q = q_bf16.shape[0]
+        elif torch.is_tensor(sparse_tokens):
+            Q = int(sparse_tokens[:, 0].max().item()) + 1 if sparse_tokens.numel() else 1
+        else:
+            Q = len(sparse_tokens[0])
+        return self.bm25_field_scores(sparse_tokens, Q)
+
+    def bm25_field_scores(self, sparse_tokens, Q: int) -> torch.Tensor:
+        """fp32 [Q, F_s, ld>=N]: what ``get_scores`` returns for every (query, sparse field), on the device."""
+        out = self.bm25.field_scores(self._bm25_entries(sparse_tokens), Q)
+        self.last_launches = self.bm25.last_launches
+        return out
+
     # ------------------------------------------------------------------ exhaustive fused search
     @torch.no_grad()
     def search(self, q_vecs, q_emb: Optional[torch.Tensor] = None, sparse: Optional[torch.Tensor] = None,
-               top_k: Optional[int] = None, return_keys: bool = False, impl: Optional[str] = None, sparse_coo=None):
+               top_k: Optional[int] = None, return_keys: bool = False, impl: Optional[str] = None, sparse_coo=None,
+               sparse_tokens=None, batch: Optional[int] = None):
         """Exhaustive multi-field top-k.
 
         q_vecs [Q,dim]: query vectors for the dense dots (rounded to bf16);
@@ -215,20 +268,38 @@ class MultiFieldRetriever:
         sparse_coo     : instead of ``sparse``: (keys int32 [nnz,2] = (query row, GLOBAL doc row), vals f16/f32 [nnz],
                         field_offsets [Fs+1]) on the device - the reference's precomputed-BM25 layout
                         (``PrecomputedSparseScores.batch``); pairs that are absent score 0 (index.py:120-125).
+        sparse_tokens  : instead of ``sparse`` when the retriever holds BM25 indices (``sparse_indices=``): the query
+                        tokens, either ``tokens[j][q]`` = token list (str or vocabulary ids) of query q for sparse
+                        field j, or the prebuilt int32 [n,3] entry tensor of ``BM25FieldSet.entries`` - the sparse
+                        fields are then scored on the device (bm25s ``get_scores``, index.py:72-76).
+        batch          : number of queries, needed only for a sparse-only retriever fed with an entry tensor.
         Returns (scores [Q,k] fp32, ids [Q,k] int64) sorted by (score desc, id asc); with
         return_keys also the packed uint64 keys (as int64) used for cross-shard merging."""
         k = top_k or self.top_k
         if self.corpus is not None:
             q_bf16 = self.corpus.prepare_queries(q_vecs)
             Q = q_bf16.shape[0]
+        elif sparse is not None:
+            q_bf16, Q = None, sparse.shape[0]
+        elif batch is not None:
+            q_bf16, Q = None, int(batch)
+        elif sparse_tokens is not None and not torch.is_tensor(sparse_tokens):
+            q_bf16, Q = None, len(sparse_tokens[0])
+        elif q_emb is not None:
+            q_bf16, Q = None, int(q_emb.shape[0])
         else:
-            q_bf16, Q = None, (sparse.shape[0] if sparse is not None else int(q_emb.shape[0]))
+            raise ValueError("cannot infer the batch size: pass batch= (sparse-only retriever with an entry tensor)")
         if self.mixture.query_cond:
             qe = q_emb if q_emb is not None else (q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs))
             qe = qe.to(self.device).float()
         else:
             qe = None
         w = self.mixture.field_weights(qe, self.mask, batch=Q)
+        if sparse_tokens is not None:
+            ent = self._bm25_entries(sparse_tokens)
+            scores, ids, keys = self._score_topk(q_bf16, w, None, nv.F16, k, 0, self.n_dense, self.n_sparse,
+                                                 want_keys=return_keys, impl=impl, bm25_entries=ent)
+            return (scores, ids, keys) if return_keys else (scores, ids)
         if sparse_coo is not None:
             if self.n_sparse == 0:
                 raise ValueError("retriever has no sparse fields")
@@ -346,15 +417,63 @@ class MultiFieldRetriever:
         self.last_launches = nv.lib().mfar_last_launch_count()
         return out_scores, out_ids
 
+    def search_host_bm25(self, q_vecs_host: Optional[torch.Tensor], q_emb_host: Optional[torch.Tensor],
+                         entries_host: torch.Tensor, top_k: Optional[int] = None,
+                         out_scores: Optional[torch.Tensor] = None, out_ids: Optional[torch.Tensor] = None,
+                         impl: Optional[str] = None, batch: Optional[int] = None):
+        """``search_host`` for a retriever whose sparse fields are device-resident BM25 indices
+        (``mfar_search_host_bm25``): per batch only the query vectors / embedding and the int32 [n,3] token entries
+        (``BM25FieldSet.entries_host``, ideally pinned) cross PCIe."""
+        if self.bm25 is None:
+            raise ValueError("search_host_bm25 needs a retriever built with sparse_indices=[DeviceBM25, ...]")
+        k = top_k or self.top_k
+        c = self.corpus
+        if q_vecs_host is not None:
+            Q = q_vecs_host.shape[0]
+        elif q_emb_host is not None:
+            Q = q_emb_host.shape[0]
+        else:
+            Q = int(batch)
+        if c is not None and (q_vecs_host.dtype != torch.bfloat16 or q_vecs_host.shape[1] != c.dim_pad
+                              or q_vecs_host.is_cuda):
+            raise ValueError("q_vecs_host must be a host bf16 [Q, dim_pad] tensor")
+        E = self.mixture.weight.shape[0] if self.mixture.query_cond else 0
+        if self.mixture.query_cond and (q_emb_host is None or q_emb_host.dtype != torch.float32):
+            raise ValueError("q_emb_host must be a host fp32 [Q,E] tensor")
+        if entries_host.is_cuda or entries_host.dtype != torch.int32 or entries_host.dim() != 2 \
+                or entries_host.shape[1] != 3 or not entries_host.is_contiguous():
+            raise ValueError("entries_host must be a contiguous host int32 [n,3] tensor")
+        n_ent = entries_host.shape[0]
+        need = nv.lib().mfar_search_host_bm25_scratch_bytes(Q, c.dim_pad if c else 0, E, self.n_dense, self.n_sparse,
+                                                            self.n_docs, n_ent, k)
+        if self._host_scratch is None or self._host_scratch.numel() < need:
+            self._host_scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if out_scores is None:
+            out_scores = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+        if out_ids is None:
+            out_ids = torch.empty((Q, k), dtype=torch.int64).pin_memory()
+        W = self.mixture.weight.detach().contiguous().float()
+        m = self.mask.reshape(-1).contiguous().float()
+        b = self.bm25
+        nv.check(nv.lib().mfar_search_host_bm25(
+            nv.ptr(c.data) if c else 0, self.n_docs, c.n_fields if c else 0, 0, self.n_dense, c.dim_pad if c else 0,
+            nv.ptr(q_vecs_host), nv.ptr(q_emb_host), Q, E, nv.ptr(W), nv.ptr(m), int(self.mixture.query_cond),
+            b.indptr, b.indices, b.data, b.vocab, self.n_sparse, nv.ptr(entries_host) if n_ent else 0, n_ent,
+            self.doc_id_base, k, nv.ptr(out_scores), nv.ptr(out_ids), nv.ptr(self._host_scratch),
+            self._host_scratch.numel(), nv.IMPL[impl or self.impl], nv.stream()), "search_host_bm25")
+        self.last_launches = nv.lib().mfar_last_launch_count()
+        return out_scores, out_ids
+
     # ------------------------------------------------------------------ per-field top-k (index.py:181-222)
     @torch.no_grad()
     def per_field_topk(self, q_vecs, sparse: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
-                       zero_init: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+                       zero_init: bool = True, sparse_tokens=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """What ``index.retrieve_batch(queries, top_k)`` returns for every field, in field order:
         (scores [F,Q,k], rows [F,Q,k]).  Dense fields reproduce the reference's (0.0, row 0) running-top-k
         initialisation (index.py:192-193) when zero_init is set."""
         k = top_k or self.top_k
         q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
+        sparse = self._sparse_from_tokens(sparse, sparse_tokens, q_bf16)
         Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
         sp, code = self._check_sparse(sparse, Q)
         ones = torch.ones((Q, 1), dtype=torch.float32, device=self.device)
@@ -375,9 +494,11 @@ class MultiFieldRetriever:
 
     # ------------------------------------------------------------------ candidate re-scoring (index.py:227-232)
     @torch.no_grad()
-    def score_candidates(self, q_vecs, rows: torch.Tensor, sparse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def score_candidates(self, q_vecs, rows: torch.Tensor, sparse: Optional[torch.Tensor] = None,
+                         sparse_tokens=None) -> torch.Tensor:
         """Per-field scores of the given local rows: [F, Q, C] (rows < 0 -> 0, index.py:112-117)."""
         q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
+        sparse = self._sparse_from_tokens(sparse, sparse_tokens, q_bf16)
         Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
         rows = rows.to(self.device, dtype=torch.int64).contiguous()
         C = rows.numel()
@@ -397,10 +518,14 @@ class MultiFieldRetriever:
     # ------------------------------------------------------------------ faithful pipeline (contrastive.py:669-704)
     @torch.no_grad()
     def union_rescore(self, q_vecs, q_emb: Optional[torch.Tensor] = None, sparse: Optional[torch.Tensor] = None,
-                      top_k: Optional[int] = None) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+                      top_k: Optional[int] = None, sparse_tokens=None
+                      ) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
         """per-field top-k -> union -> rescore -> * mask -> mixture -> top-k, per query.
         Returns per query (values [k], local rows [k])."""
         k = top_k or self.top_k
+        if sparse_tokens is not None:                                      # BM25 get_scores once per (query, field)
+            sparse = self._sparse_from_tokens(None, sparse_tokens,
+                                              None if self.corpus is None else self.corpus.prepare_queries(q_vecs))
         _, rows = self.per_field_topk(q_vecs, sparse, k)                   # [F,Q,k]
         Q = rows.shape[1]
         qv = q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs)
@@ -424,14 +549,14 @@ class MultiFieldRetriever:
 
     # ------------------------------------------------------------------ QRes emission (contrastive.py:696-704)
     def trec_eval_step(self, query_ids: Sequence[str], q_vecs, qres_output: TextIO, q_emb=None, sparse=None,
-                       mode: str = "exhaustive") -> None:
+                       mode: str = "exhaustive", sparse_tokens=None) -> None:
         if self.numeric_ids_to_keys is None:
             raise RuntimeError("trec_eval_step needs numeric_ids_to_keys to name documents")
         if mode == "exhaustive":
-            scores, ids = self.search(q_vecs, q_emb, sparse)
+            scores, ids = self.search(q_vecs, q_emb, sparse, sparse_tokens=sparse_tokens)
             scores, ids = scores.cpu().tolist(), (ids - self.doc_id_base).cpu().tolist()
         elif mode == "union_rescore":
-            v, r = self.union_rescore(q_vecs, q_emb, sparse)
+            v, r = self.union_rescore(q_vecs, q_emb, sparse, sparse_tokens=sparse_tokens)
             scores, ids = [x.cpu().tolist() for x in v], [x.cpu().tolist() for x in r]
         else:
             raise ValueError(mode)

@@ -6,7 +6,7 @@ import json
 from pathlib import Path
 from typing import Dict, Iterable, List, Optional, Tuple
 
-from ..data.index import DenseFlatIndex, PrecomputedSparseIndex
+from ..data.index import BM25sSparseIndex, DenseFlatIndex, PrecomputedSparseIndex
 from ..data.typedef import Field, FieldType
 from ..data.util import MemoryMapDict
 
@@ -79,12 +79,15 @@ class PrecomputedSparseScores:
 
 
 def read_and_create_indices(corpus_path: str, dataset_name: str, field_info: Dict[str, Field], temp_dir: str,
-                            encoder, device="cuda", sparse_scores: Optional[Dict[str, Dict[str, object]]] = None):
+                            encoder, device="cuda", sparse_scores: Optional[Dict[str, Dict[str, object]]] = None,
+                            sparse_texts: Optional[Dict[str, Dict[str, str]]] = None):
     """Same contract as the reference (modeling/util.py:73-108): returns
     ``(corpus, vectors_dict, indices_dict)``; for every dense field an (empty, to-be-filled)
     headerless fp32 memmap ``{temp_dir}/{field.name}.npy`` wrapped in MemoryMapDict + DenseFlatIndex.
-    Sparse fields get a PrecomputedSparseIndex over ``sparse_scores[field_key]`` (BM25 itself -
-    third-party bm25s in the reference - is an input to this path)."""
+    Sparse fields: with ``sparse_texts[field_key] = {doc key: formatted field text}`` (what the reference's
+    ``format_documents`` yields, modeling/util.py:102-103 - text formatting is outside this path) a device-resident
+    ``BM25sSparseIndex`` is built (modeling/util.py:104-105); otherwise a PrecomputedSparseIndex over
+    ``sparse_scores[field_key]``."""
     corpus = list(read_corpus(corpus_path))
     keys: List[str] = [x[0] for x in corpus]
     key_to_row = {k: i for i, k in enumerate(keys)}
@@ -101,7 +104,10 @@ def read_and_create_indices(corpus_path: str, dataset_name: str, field_info: Dic
             indices_dict[field_key] = DenseFlatIndex(encoder, vectors.file, numeric_ids_to_keys=keys,
                                                      keys_to_numeric_ids=key_to_row, device=device)
         elif field.field_type == FieldType.SPARSE:
-            idx = PrecomputedSparseIndex(keys, (sparse_scores or {}).get(field_key, {}), device=device)
+            if sparse_texts is not None and field_key in sparse_texts:
+                idx = BM25sSparseIndex.create(sparse_texts[field_key], dataset_name=dataset_name, device=device)
+            else:
+                idx = PrecomputedSparseIndex(keys, (sparse_scores or {}).get(field_key, {}), device=device)
             idx.name = field.name
             indices_dict[field_key] = idx
     return corpus, vectors_dict, indices_dict

@@ -68,6 +68,48 @@ def make_sparse(Q: int, Fs: int, n_docs: int, seed: int, device="cpu", dtype=tor
     return torch.where(u < 0.95, torch.zeros_like(e1), e1 + e2).to(dtype)
 
 
+# ---- synthetic BM25 fields (device-resident sparse scorer): token ids ~ Zipf(1) over a 30k vocabulary, field length
+# ~ Poisson(12) tokens; query tokens are Zipf-distributed over ranks > 20 (stop-word-like head terms never appear in
+# queries), 8 per (query, field): the union of their postings covers ~5 % of the docs - the density make_sparse uses.
+BM25_VOCAB = 30000
+BM25_DOC_LEN = 12
+BM25_QUERY_TOKENS = 8
+BM25_QUERY_MIN_RANK = 20
+
+
+def make_bm25_field(n_docs: int, seed: int, device, n_vocab: int = BM25_VOCAB, mean_len: int = BM25_DOC_LEN,
+                    doc_range: Optional[Tuple[int, int]] = None):
+    """One sparse field of the WHOLE corpus indexed on the device (idf / average length are corpus statistics), then
+    cut to ``doc_range``.  Deterministic in (n_docs, seed) so every shard count sees the same global field."""
+    from .data.bm25 import DeviceBM25
+    g = _gen(device, seed)
+    p = 1.0 / torch.arange(1, n_vocab + 1, dtype=torch.float32, device=device)
+    lens = torch.poisson(torch.full((n_docs,), float(mean_len), device=device), generator=g).clamp_(min=1).long()
+    total = int(lens.sum().item())
+    toks = torch.empty(total, dtype=torch.int64, device=device)
+    step = 1 << 24                                           # torch.multinomial draws at most 2^24 samples per call
+    for lb in range(0, total, step):
+        n = min(step, total - lb)
+        toks[lb:lb + n] = torch.multinomial(p, n, replacement=True, generator=g)
+    full = DeviceBM25(device=device).index_flat(toks, lens, n_vocab)
+    return full.shard(*doc_range) if doc_range is not None else full
+
+
+def make_bm25_query_entries(Q: int, Fs: int, seed: int, n_vocab: int = BM25_VOCAB,
+                            n_tokens: int = BM25_QUERY_TOKENS) -> torch.Tensor:
+    """HOST int32 [Q*Fs*n_tokens, 3] entries (query row, sparse field, token id), query-major like
+    ``data.bm25.token_entries``."""
+    g = _gen("cpu", seed)
+    p = 1.0 / torch.arange(1, n_vocab + 1, dtype=torch.float32)
+    p[:BM25_QUERY_MIN_RANK] = 0
+    tok = torch.multinomial(p, Q * Fs * n_tokens, replacement=True, generator=g).view(Fs, Q, n_tokens)
+    ent = torch.empty((Fs, Q, n_tokens, 3), dtype=torch.int32)
+    ent[..., 0] = torch.arange(Q, dtype=torch.int32).view(1, Q, 1)
+    ent[..., 1] = torch.arange(Fs, dtype=torch.int32).view(Fs, 1, 1)
+    ent[..., 2] = tok.int()
+    return ent.permute(1, 0, 2, 3).reshape(-1, 3).contiguous()
+
+
 def fill_packed_corpus(pc, seed: int, chunk_docs: int = 65536, doc_offset: int = 0) -> None:
     """Generate the corpus ON DEVICE straight into a PackedCorpus (config 5 is 122.9 GB: it cannot come
     from host RAM).  Doc n's vectors depend only on (seed, global chunk index), so shards of a

@@ -1,0 +1,245 @@
+"""Device BM25 scorer (csrc/bm25.cu) vs the BM25 oracle (oracle/bm25_oracle.py), every call through the C ABI.
+
+bm25s is a third-party dependency of the reference that is unavailable here - the oracle restates its published
+algorithm (parity unpinned; tests/test_bm25_cpu.py pins the restatement against hand-computed values).
+Bars: index structure (indptr / indices) bit-exact; score-matrix values bit-exact up to 1 fp32 ulp where the device
+``log`` differs from libm; query score vectors within 2e-6 relative (fp32 sums in a different order); hybrid top-k
+by tests/parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import bm25_oracle as B
+import mfar_oracle as O
+from parity import assert_topk_parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _corpus(seed, n_docs, n_vocab, mean_len):
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, n_vocab + 1); p /= p.sum()
+    return [rng.choice(n_vocab, size=max(1, rng.poisson(mean_len)), p=p).tolist() for _ in range(n_docs)]
+
+
+def _queries(seed, Q, n_vocab, n_tok, oov=True):
+    rng = np.random.default_rng(seed)
+    p = 1.0 / np.arange(1, n_vocab + 1); p /= p.sum()
+    out = []
+    for q in range(Q):
+        toks = rng.choice(n_vocab, size=rng.integers(1, n_tok + 1), p=p).tolist()
+        if q % 3 == 0:
+            toks.append(toks[0])                                     # a repeated token counts twice
+        if oov and q % 4 == 1:
+            toks.insert(1, n_vocab + 5)                              # not in the vocabulary: skipped
+        out.append(toks)
+    return out
+
+
+def _to_oracle(ix):
+    s = ix.scores
+    return {"data": s["data"].cpu().numpy(), "indices": s["indices"].cpu().numpy(),
+            "indptr": s["indptr"].cpu().numpy(), "num_docs": ix.num_docs, "n_vocab": ix.n_vocab}
+
+
+def _mods():
+    from mfar_b200.data.bm25 import DeviceBM25
+    from mfar_b200.modeling.retrieval import MultiFieldRetriever, PackedCorpus
+    from mfar_b200.modeling.weighting import LinearWeights
+    return DeviceBM25, MultiFieldRetriever, PackedCorpus, LinearWeights
+
+
+@pytest.mark.parametrize("seed,n_docs,n_vocab,mean_len", [(0, 50, 30, 6), (1, 3000, 400, 12), (2, 777, 5000, 4)])
+def test_index_build_matches_oracle(seed, n_docs, n_vocab, mean_len):
+    DeviceBM25 = _mods()[0]
+    corpus = _corpus(seed, n_docs, n_vocab, mean_len)
+    want = B.build_index(corpus, n_vocab)
+    ix = DeviceBM25(device=DEV).index(corpus, vocab=n_vocab)
+    got = _to_oracle(ix)
+    assert got["num_docs"] == n_docs and got["n_vocab"] == n_vocab
+    assert np.array_equal(got["indptr"], want["indptr"])
+    assert np.array_equal(got["indices"], want["indices"])
+    ulp = np.abs(got["data"].view(np.int32).astype(np.int64) - want["data"].view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1, f"score matrix differs by {ulp.max()} ulp"
+    assert (ulp == 0).mean() > 0.999
+
+
+def test_get_scores_and_retrieve_match_oracle():
+    DeviceBM25 = _mods()[0]
+    n_docs, n_vocab = 5000, 600
+    corpus = _corpus(5, n_docs, n_vocab, 15)
+    ix = DeviceBM25(device=DEV).index(corpus, vocab=n_vocab)
+    oidx = _to_oracle(ix)
+    queries = _queries(6, 17, n_vocab, 8)
+    got = ix.get_scores_batch(queries).cpu().numpy()
+    assert got.shape == (17, n_docs)
+    for q, toks in enumerate(queries):
+        want = B.get_scores(oidx, toks)
+        np.testing.assert_allclose(got[q], want, rtol=2e-6, atol=1e-6)
+        assert np.array_equal(got[q] == 0, want == 0)                # untouched docs stay exactly zero
+    one = ix.get_scores(queries[3])
+    assert isinstance(one, np.ndarray) and one.dtype == np.float32 and np.array_equal(one, got[3])
+    rows, vals = ix.retrieve(queries, k=100)
+    all_s = np.stack([B.get_scores(oidx, t) for t in queries])
+    assert_topk_parity(vals, rows, all_s, 100, rtol=2e-5)
+    with pytest.raises(ValueError):
+        ix.retrieve(queries, k=n_docs + 1)
+    with pytest.raises(ValueError):
+        ix.get_scores("not a list")
+
+
+def test_many_entries_and_long_postings_cross_chunk_boundaries():
+    """> 1024 entries (several rounds of the plan kernel's scan) and postings lists far longer than one 4096-posting
+    scatter chunk, next to 1-posting lists."""
+    DeviceBM25, MultiFieldRetriever, _, LinearWeights = _mods()
+    n_docs, n_vocab, Fs, Q = 60000, 3000, 3, 96
+    fields, oidx = [], []
+    for j in range(Fs):
+        rng = np.random.default_rng(10 + j)
+        p = 1.0 / np.arange(1, n_vocab + 1) ** 1.1; p /= p.sum()
+        lens = np.maximum(1, rng.poisson(8, size=n_docs))
+        flat = rng.choice(n_vocab, size=int(lens.sum()), p=p)
+        ix = DeviceBM25(device=DEV).index_flat(torch.from_numpy(flat), torch.from_numpy(lens), n_vocab)
+        fields.append(ix); oidx.append(_to_oracle(ix))
+    tokens = [_queries(20 + j, Q, n_vocab, 14) for j in range(Fs)]
+    W = torch.randn(Fs, 1, generator=torch.Generator().manual_seed(3))
+    layer = LinearWeights(Fs, 1)
+    with torch.no_grad():
+        layer.weight.copy_(W)
+    r = MultiFieldRetriever(None, layer.to(DEV), top_k=100, device=DEV, sparse_indices=fields)
+    ent = r.bm25.entries(tokens)
+    assert ent.shape[0] > 2048
+    per_field = r.bm25_field_scores(ent, Q)[:, :, :n_docs].cpu().numpy()          # [Q,Fs,N]
+    w = torch.softmax(W.t(), dim=1).numpy()[0]
+    all_s = np.zeros((Q, n_docs), np.float32)
+    for j in range(Fs):
+        for q in range(Q):
+            want = B.get_scores(oidx[j], tokens[j][q])
+            np.testing.assert_allclose(per_field[q, j], want, rtol=3e-6, atol=1e-6)
+            all_s[q] += w[j] * want
+    s, i = r.search(None, sparse_tokens=ent, batch=Q)
+    assert_topk_parity(s.cpu().numpy(), i.cpu().numpy(), all_s, 100, rtol=2e-5)
+    assert r.last_launches >= 4                                      # memset + plan + scatter + scoring + merge
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05", "tcgen05_qs"])
+def test_hybrid_search_with_device_bm25_vs_oracle(impl):
+    DeviceBM25, MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    N, d, Fd, Fs, Q, k, V = 4000, 128, 3, 2, 70 if impl == "tcgen05_qs" else 9, 100, 500
+    g = torch.Generator().manual_seed(11)
+    mu = torch.randn(d, generator=g)
+    dense = [O.round_bf16(torch.randn(N, d, generator=g) + 0.5 * mu) for _ in range(Fd)]
+    qv = O.round_bf16(torch.randn(Q, d, generator=g) + 0.5 * mu)
+    Wm = 0.05 * torch.randn(d, Fd + Fs, generator=g)
+    bm = [DeviceBM25(device=DEV).index(_corpus(30 + j, N, V, 10), vocab=V) for j in range(Fs)]
+    tokens = [_queries(40 + j, Q, V, 6) for j in range(Fs)]
+    tokens[1][2] = []                                                # a query with no tokens for one field
+    layer = LinearWeights(d, Fd + Fs, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(Wm)
+    r = MultiFieldRetriever(PackedCorpus.from_fields(dense, DEV), layer.to(DEV), top_k=k, impl=impl,
+                            sparse_indices=bm)
+    sp = torch.stack([torch.from_numpy(np.stack([B.get_scores(_to_oracle(bm[j]), tokens[j][q]) for j in range(Fs)]))
+                      for q in range(Q)])                            # [Q,Fs,N] oracle BM25 vectors
+    ref = O.exhaustive_scores(qv, dense, sp, O.mixture_weights(qv, Wm, True))
+    s, i = r.search(qv.to(DEV), qv.to(DEV), sparse_tokens=tokens)
+    assert_topk_parity(s.cpu().numpy(), i.cpu().numpy(), ref.numpy(), k)
+    # the same search fed with the device-computed per-field vectors as a dense tensor agrees
+    s2, i2 = r.search(qv.to(DEV), qv.to(DEV), sparse=r.bm25_field_scores(tokens, Q))
+    assert_topk_parity(s2.cpu().numpy(), i2.cpu().numpy(), ref.numpy(), k)
+    # masking a sparse field removes its contribution (contrastive.py:686)
+    r.mask_field([Fd + 1])
+    wm = O.mixture_weights(qv, Wm, True).clone(); wm[:, Fd + 1] = 0
+    s3, i3 = r.search(qv.to(DEV), qv.to(DEV), sparse_tokens=tokens)
+    assert_topk_parity(s3.cpu().numpy(), i3.cpu().numpy(), O.exhaustive_scores(qv, dense, sp, wm).numpy(), k)
+
+
+def test_search_host_bm25_equals_device_search():
+    DeviceBM25, MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    N, d, Fd, Fs, Q, V = 3000, 768, 2, 2, 8, 300
+    g = torch.Generator().manual_seed(12)
+    dense = [O.round_bf16(torch.randn(N, d, generator=g)) for _ in range(Fd)]
+    qv = O.round_bf16(torch.randn(Q, d, generator=g))
+    bm = [DeviceBM25(device=DEV).index(_corpus(50 + j, N, V, 9), vocab=V) for j in range(Fs)]
+    tokens = [_queries(60 + j, Q, V, 5) for j in range(Fs)]
+    layer = LinearWeights(d, Fd + Fs, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(0.05 * torch.randn(d, Fd + Fs, generator=g))
+    r = MultiFieldRetriever(PackedCorpus.from_fields(dense, DEV), layer.to(DEV), sparse_indices=bm)
+    s, i = r.search(qv.to(DEV), qv.to(DEV), sparse_tokens=tokens)
+    ent = torch.from_numpy(r.bm25.entries_host(tokens)).pin_memory()
+    hs, hi = r.search_host_bm25(qv.to(torch.bfloat16).pin_memory(), qv.float().pin_memory(), ent)
+    assert r.last_launches >= 6
+    assert torch.equal(hi, i.cpu())
+    torch.testing.assert_close(hs, s.cpu(), rtol=2e-6, atol=1e-6)    # fp32 atomics: summation order may differ
+    # no tokens at all: the sparse fields contribute nothing
+    es, ei = r.search_host_bm25(qv.to(torch.bfloat16).pin_memory(), qv.float().pin_memory(),
+                                torch.zeros((0, 3), dtype=torch.int32))
+    w = O.mixture_weights(qv, layer.weight.detach().cpu(), True)
+    ref = O.exhaustive_scores(qv, dense, torch.zeros(Q, Fs, N), w)
+    assert_topk_parity(es.numpy(), ei.numpy(), ref.numpy(), 100)
+
+
+def test_doc_range_shards_merge_to_the_single_shard_result():
+    DeviceBM25, MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    from mfar_b200 import _native as nv
+    N, d, V, Q, k = 5000, 64, 400, 6, 100
+    g = torch.Generator().manual_seed(13)
+    dense = [O.round_bf16(torch.randn(N, d, generator=g))]
+    qv = O.round_bf16(torch.randn(Q, d, generator=g))
+    full = DeviceBM25(device=DEV).index(_corpus(70, N, V, 10), vocab=V)
+    tokens = [_queries(71, Q, V, 6)]
+    layer = LinearWeights(d, 2, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(0.05 * torch.randn(d, 2, generator=g))
+    layer = layer.to(DEV)
+    one = MultiFieldRetriever(PackedCorpus.from_fields(dense, DEV), layer, sparse_indices=[full])
+    s1, i1 = one.search(qv.to(DEV), qv.to(DEV), sparse_tokens=tokens)
+    keys = []
+    for lo, hi in [(0, 1700), (1700, 1701 + 1000), (2701, N)]:
+        part = MultiFieldRetriever(PackedCorpus.from_fields([dense[0][lo:hi]], DEV), layer, doc_id_base=lo,
+                                   sparse_indices=[full.shard(lo, hi)])
+        _, _, kk = part.search(qv.to(DEV), qv.to(DEV), sparse_tokens=tokens, return_keys=True)
+        keys.append(kk)
+    allk = torch.stack(keys).contiguous()
+    ms = torch.empty((Q, k), dtype=torch.float32, device=DEV)
+    mi = torch.empty((Q, k), dtype=torch.int64, device=DEV)
+    nv.check(nv.lib().mfar_topk_merge(nv.ptr(allk), 3, Q, k, k, 0, nv.ptr(ms), nv.ptr(mi), nv.stream()), "merge")
+    assert torch.equal(mi, i1)
+    torch.testing.assert_close(ms, s1, rtol=2e-6, atol=1e-6)
+
+
+def test_bm25s_sparse_index_api(tmp_path):
+    from mfar_b200.data.index import BM25sSparseIndex
+    docs = {f"d{i}": t for i, t in enumerate([
+        "protein kinase binding assay", "kinase inhibitor for the treatment of cancer", "the cat sat on the mat",
+        "cancer cancer cancer research protein", "binding of zinc to protein domains", "an unrelated document"])}
+    idx = BM25sSparseIndex.create(docs, dataset_name="prime", device=DEV)
+    assert idx.index_limit == 12000 and idx.keys == list(docs)
+    toks = [B.tokenize(t) for t in docs.values()]
+    vocab = idx.index.vocab_dict
+    oidx = B.build_index([[vocab[t] for t in d] for d in toks], len(vocab))
+    q = "Protein kinase and cancer, cancer?"
+    want = B.get_scores(oidx, [vocab[t] for t in B.tokenize(q) if t in vocab])
+    got = idx.get_scores(q)
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+    assert idx.get_scores(q) is got                                  # per-query cache (index.py:71)
+    res = idx.retrieve_batch([q, "zinc"], top_k=3)
+    assert [k for k, _ in res[0]] == [f"d{i}" for i in np.lexsort((np.arange(6), -want))[:3]]
+    assert res[1][0][0] == "d4" and idx.retrieve("zinc", 2)[0][0] == "d4"
+    sb = idx.score_batch([q, "zinc"], ["d3", "nope", "d0"])
+    assert tuple(sb.shape) == (2, 3) and sb[0, 1] == 0 and sb[1, 1] == 0
+    np.testing.assert_allclose(sb[0].numpy()[[0, 2]], want[[3, 0]], rtol=2e-6)
+    assert np.allclose(idx.score(q, ["d1", "d4"]), want[[1, 4]], rtol=2e-6)
+    idx.set_safe_docs({0, 3})
+    assert set(idx.get_scores_sparse(q)) == {0, 3}
+    assert idx.score_batch_with_cache([7], ["d1", "d2"], {7: {1: 2.5}}).tolist() == [[2.5, 0]]
+    # bm25s on-disk layout round trip (index.py:147-157)
+    idx.save(str(tmp_path / "ix"))
+    for fn in ("data.csc.index.npy", "indices.csc.index.npy", "indptr.csc.index.npy", "vocab.index.json",
+               "params.index.json"):
+        assert (tmp_path / "ix" / "index" / fn).exists()
+    back = BM25sSparseIndex.load(str(tmp_path / "ix"), device=DEV)
+    assert back.keys == idx.keys
+    np.testing.assert_array_equal(back.get_scores(q), got)
