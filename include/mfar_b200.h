@@ -256,6 +256,36 @@ MFAR_API int mfar_search_host_bm25(const void* corpus, int64_t n_docs, int corpu
                                    float* out_scores_host, int64_t* out_ids_host, void* scratch,
                                    size_t scratch_bytes, int impl, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-time scorer (fp32, forward + backward).  Replaces
+ *   DecomposedContrastiveLoss.compute_query_doc_field_components   mfar/modeling/losses.py:176-188
+ *   DecomposedContrastiveLoss.compute_doc_query_scores             mfar/modeling/losses.py:199-202
+ *   the autograd of LinearWeights.forward                          mfar/modeling/weighting.py:17-29
+ * Doc n = (p, s) with p = n / inner, s = n % inner; the E-vector of (doc n, field f) starts at
+ * docs + p*stride_p + f*stride_f + s*stride_s (in elements): d_pos [P,F,E] is inner = 1, stride_p = F*E,
+ * stride_f = E; d_neg [P,F,Neg,E] is inner = Neg, stride_p = F*Neg*E, stride_f = Neg*E, stride_s = E, which yields
+ * the doc order of d_neg.permute(0,2,1,3).view(1, P*Neg, F, E) (losses.py:186) without a copy.
+ * E % 4 == 0, E <= 1024, rows 16-byte aligned.
+ * ------------------------------------------------------------------------------------------ */
+/* comp[b, n, f] = <q[b,:], doc[n,f,:]> / temperature            comp: fp32 [B, N, F] */
+MFAR_API int mfar_field_components_fwd(const float* q, int B, int E, const float* docs, int64_t N, int F,
+                                       int64_t inner, int64_t stride_p, int64_t stride_f, int64_t stride_s,
+                                       float temperature, float* comp, void* stream);
+/* dq[b,:]     = sum_{n,f} dcomp[b,n,f] * doc[n,f,:] / temperature      (dq: fp32 [B,E], overwritten; may be NULL)
+ * ddocs[n,f,:] = sum_b    dcomp[b,n,f] * q[b,:]     / temperature      (ddocs: same layout as docs; may be NULL) */
+MFAR_API int mfar_field_components_bwd(const float* q, int B, int E, const float* docs, int64_t N, int F,
+                                       int64_t inner, int64_t stride_p, int64_t stride_f, int64_t stride_s,
+                                       float temperature, const float* dcomp, float* dq, float* ddocs, void* stream);
+/* Backward of out[b,s] = sum_f w[b,f] x[b,s,f], w = softmax(q_emb @ W) (query_cond) or softmax(W^T) (W is [F,1]):
+ *   dx[b,s,f] = g[b,s] w[b,f]            (dx may be NULL)
+ *   dW        = q_emb^T dlogit  ([E,F])  or  sum_b dlogit[b,:] ([F,1]),   dlogit = softmax backward of sum_s g x
+ *   dq[b,:]   = dlogit[b,:] W^T          (query_cond only; may be NULL)
+ * w: the forward's weights, fp32 [w_rows, F] with w_rows = B or 1 (mfar_mixture_weights without a mask);
+ * dlogit_scratch: fp32 [B, F]. */
+MFAR_API int mfar_mixture_bwd(const float* x, const float* q_emb, const float* W, const float* w, int w_rows,
+                              const float* g, int B, int S, int E, int F, int query_cond, float* dx, float* dW,
+                              float* dq, float* dlogit_scratch, void* stream);
+
 /* Number of kernels the last mfar_score_topk call on this thread launched (bench bookkeeping). */
 MFAR_API int mfar_last_launch_count(void);
 

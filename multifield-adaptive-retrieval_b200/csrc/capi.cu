@@ -520,6 +520,50 @@ int mfar_search_host_bm25(const void* corpus, int64_t n_docs, int corpus_fields,
   return MFAR_OK;
 }
 
+static int check_doc_layout(const float* q, int B, int E, const float* docs, int64_t N, int F, int64_t inner,
+                            int64_t stride_p, int64_t stride_f, int64_t stride_s, float temperature) {
+  if (!q || !docs || B <= 0 || N <= 0 || inner <= 0 || N % inner != 0 || !(temperature > 0.f)) return MFAR_ERR_ARG;
+  if (F <= 0 || F > MFAR_MAX_FIELDS || E <= 0 || E % 4 != 0 || E > 1024) return MFAR_ERR_SHAPE;
+  if (stride_p % 4 || stride_f % 4 || stride_s % 4 || reinterpret_cast<uintptr_t>(docs) % 16 ||
+      reinterpret_cast<uintptr_t>(q) % 16)
+    return MFAR_ERR_ARG;
+  return MFAR_OK;
+}
+
+int mfar_field_components_fwd(const float* q, int B, int E, const float* docs, int64_t N, int F, int64_t inner,
+                              int64_t stride_p, int64_t stride_f, int64_t stride_s, float temperature, float* comp,
+                              void* stream) {
+  if (int rc = check_doc_layout(q, B, E, docs, N, F, inner, stride_p, stride_f, stride_s, temperature)) return rc;
+  if (!comp) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  const DocLayout L{inner, stride_p, stride_f, stride_s};
+  return launch_field_components_fwd(q, B, E, docs, N, F, L, temperature, comp, static_cast<cudaStream_t>(stream));
+}
+
+int mfar_field_components_bwd(const float* q, int B, int E, const float* docs, int64_t N, int F, int64_t inner,
+                              int64_t stride_p, int64_t stride_f, int64_t stride_s, float temperature,
+                              const float* dcomp, float* dq, float* ddocs, void* stream) {
+  if (int rc = check_doc_layout(q, B, E, docs, N, F, inner, stride_p, stride_f, stride_s, temperature)) return rc;
+  if (!dcomp || (!dq && !ddocs)) return MFAR_ERR_ARG;
+  if ((dq && reinterpret_cast<uintptr_t>(dq) % 16) || (ddocs && reinterpret_cast<uintptr_t>(ddocs) % 16))
+    return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  const DocLayout L{inner, stride_p, stride_f, stride_s};
+  return launch_field_components_bwd(q, B, E, docs, N, F, L, temperature, dcomp, dq, ddocs,
+                                     static_cast<cudaStream_t>(stream));
+}
+
+int mfar_mixture_bwd(const float* x, const float* q_emb, const float* W, const float* w, int w_rows, const float* g,
+                     int B, int S, int E, int F, int query_cond, float* dx, float* dW, float* dq,
+                     float* dlogit_scratch, void* stream) {
+  if (!x || !W || !w || !g || !dW || !dlogit_scratch || B <= 0 || S < 0) return MFAR_ERR_ARG;
+  if (query_cond && (!q_emb || E <= 0)) return MFAR_ERR_ARG;
+  if (F <= 0 || F > MFAR_MAX_FIELDS || (w_rows != 1 && w_rows != B)) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  return launch_mixture_bwd(x, q_emb, W, w, w_rows, g, B, S, E, F, query_cond, dx, dW, query_cond ? dq : nullptr,
+                            dlogit_scratch, static_cast<cudaStream_t>(stream));
+}
+
 int mfar_last_launch_count(void) { return t_last_launches; }
 
 int mfar_profile_enable(int on) {

@@ -47,6 +47,18 @@ int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, in
                           const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
                           float* out_scores, int64_t* out_ids, cudaStream_t st);
 
+// Training-time scorer (train.cu).  Doc n = (p, s), p = n / inner, s = n % inner, row of field f at
+// docs + p*stride_p + f*stride_f + s*stride_s (elements).
+struct DocLayout { long long inner, stride_p, stride_f, stride_s; };
+int launch_field_components_fwd(const float* q, int B, int E, const float* docs, long long N, int F,
+                                const DocLayout& L, float temperature, float* comp, cudaStream_t st);
+int launch_field_components_bwd(const float* q, int B, int E, const float* docs, long long N, int F,
+                                const DocLayout& L, float temperature, const float* dcomp, float* dq, float* ddocs,
+                                cudaStream_t st);
+int launch_mixture_bwd(const float* x, const float* q, const float* W, const float* w, int w_rows, const float* g,
+                       int B, int S, int E, int F, int query_cond, float* dx, float* dW, float* dq, float* dlogit,
+                       cudaStream_t st);
+
 // Arguments common to both scoring kernels (all device pointers).
 struct ScoreArgs {
   const void* corpus;       // packed bf16 [tiles][corpus_fields][128][dim]

@@ -19,7 +19,7 @@ MAX_FIELDS = 64
 
 _lib = None
 
-_vp, _i, _i64, _sz, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
+_vp, _i, _i64, _sz, _f64, _f32 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double, C.c_float
 
 # name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
 PROTOTYPES = {
@@ -53,6 +53,9 @@ PROTOTYPES = {
     "mfar_search_host_bm25_scratch_bytes": (_sz, [_i, _i, _i, _i, _i, _i64, _i64, _i]),
     "mfar_search_host_bm25": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i,
                                    _vp, _i64, _i64, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "mfar_field_components_fwd": (_i, [_vp, _i, _i, _vp, _i64, _i, _i64, _i64, _i64, _i64, _f32, _vp, _vp]),
+    "mfar_field_components_bwd": (_i, [_vp, _i, _i, _vp, _i64, _i, _i64, _i64, _i64, _i64, _f32, _vp, _vp, _vp, _vp]),
+    "mfar_mixture_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "mfar_last_launch_count": (_i, []),
     "mfar_profile_enable": (_i, [_i]),
     "mfar_profile_collect": (_i, [_vp, _i]),

@@ -209,3 +209,32 @@ def test_mask_sweep_plan_follows_mask_fields_command():
     for (label, idx), name in zip(plan[3 + F:], names):
         assert label == f"name:{name}" and len(idx) == 2            # one dense + one sparse column per name
     assert len(MultiFieldRetriever.mask_sweep_plan(resolve_fields("all_dense", "mag"))) == 1 + 5 + 1 + 5
+
+
+def test_every_package_module_imports_without_gpu():
+    import importlib
+    for name in ("mfar_b200", "mfar_b200._native", "mfar_b200.dist", "mfar_b200.synth", "mfar_b200.data.bm25",
+                 "mfar_b200.data.index", "mfar_b200.data.schema", "mfar_b200.data.trec", "mfar_b200.data.typedef",
+                 "mfar_b200.data.util", "mfar_b200.modeling.losses", "mfar_b200.modeling.retrieval",
+                 "mfar_b200.modeling.util", "mfar_b200.modeling.weighting"):
+        importlib.import_module(name)
+
+
+def test_training_scorer_refuses_cpu_tensors_and_bad_layouts():
+    from mfar_b200 import _native as nv
+    from mfar_b200.modeling import losses as L
+    with pytest.raises(RuntimeError):
+        L.field_components(torch.zeros(2, 8), torch.zeros(3, 2, 8), 1.0)
+    assert L._layout(torch.zeros(5, 3, 8)) == (5, 3, 1, 24, 8, 0)
+    assert L._layout(torch.zeros(5, 3, 4, 8)) == (20, 3, 4, 96, 32, 8)
+    with pytest.raises(ValueError):
+        L._layout(torch.zeros(5, 8))
+    lib = nv.lib()
+    fake = 0x1000
+    # argument checks precede device work: E not a multiple of 4, E > 1024, N not a multiple of inner, T <= 0
+    assert lib.mfar_field_components_fwd(fake, 2, 6, fake, 4, 2, 1, 12, 6, 0, 1.0, fake, None) == 2
+    assert lib.mfar_field_components_fwd(fake, 2, 2048, fake, 4, 2, 1, 4096, 2048, 0, 1.0, fake, None) == 2
+    assert lib.mfar_field_components_fwd(fake, 2, 8, fake, 5, 2, 2, 32, 16, 8, 1.0, fake, None) == 1
+    assert lib.mfar_field_components_fwd(fake, 2, 8, fake, 4, 2, 1, 16, 8, 0, 0.0, fake, None) == 1
+    assert lib.mfar_field_components_bwd(fake, 2, 8, fake, 4, 2, 1, 16, 8, 0, 1.0, fake, None, None, None) == 1
+    assert lib.mfar_mixture_bwd(fake, fake, fake, fake, 3, fake, 2, 4, 8, 2, 1, None, fake, None, fake, None) == 2
