@@ -201,6 +201,9 @@ def main():
     ap.add_argument("--sparse-mode", default="precomputed", choices=["precomputed", "bm25"],
                     help="sparse fields as precomputed [Q,Fs,N] f16 score tensors (north_star (2)) or scored on the "
                          "device from query tokens against HBM-resident BM25 postings (SURVEY 8f-3)")
+    ap.add_argument("--graph", action="store_true",
+                    help="N=1: replay the device-resident step as one CUDA graph (GraphedSearch); the scoring kernel's "
+                         "own duration for the roofline is taken from a short eager pass")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
@@ -239,6 +242,11 @@ def main():
         return
 
     # ------------------------------------------------------------------ our arm
+    # Native libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout, so fd 1
+    # points at stderr until that line is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA sm_100 device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
@@ -304,10 +312,38 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphs = {}
+
+    def step(batch):
+        qv, qe, sp, ent = batch
+        if args.graph and world == 1:
+            gs = graphs.get(qv.shape[0])
+            if gs is None:
+                from mfar_b200.modeling.retrieval import GraphedSearch
+                gs = graphs[qv.shape[0]] = GraphedSearch(
+                    retr, qv.shape[0], sparse="bm25" if bm25_mode else ("dense" if n_sparse else "none"),
+                    max_entries=0 if ent is None else ent.shape[0], sparse_ld=None if sp is None else sp.shape[2])
+            gs(qv, qe, sparse=sp, entries=ent)
+            return gs.launches
+        sharded.search(qv, qe, sp, sparse_tokens=ent)
+        return retr.last_launches + 1 + 1                   # + mixture-weights kernel + cross-shard merge kernel
+
     def run_device(pool, steps, warmup, profile=False):
+        if args.graph and world == 1 and profile:           # kernel duration from a short eager pass
+            nv.check(nv.lib().mfar_profile_enable(1))
+            for i in range(3):
+                qv, qe, sp, ent = pool[i % len(pool)]
+                sharded.search(qv, qe, sp, sparse_tokens=ent)
+            torch.cuda.synchronize()
+            buf0 = (ctypes.c_float * 256)()
+            n0 = nv.lib().mfar_profile_collect(ctypes.addressof(buf0), 256)
+            eager_kern_ms = [buf0[i] for i in range(max(n0, 0))]
+            nv.lib().mfar_profile_enable(0)
+            profile = False
+        else:
+            eager_kern_ms = None
         for i in range(warmup):
-            qv, qe, sp, ent = pool[i % len(pool)]
-            sharded.search(qv, qe, sp, sparse_tokens=ent)
+            step(pool[i % len(pool)])
         barrier()
         if profile:
             nv.check(nv.lib().mfar_profile_enable(1))
@@ -318,9 +354,7 @@ def main():
             torch.cuda.profiler.start()
         e0.record()
         for i in range(steps):
-            qv, qe, sp, ent = pool[i % len(pool)]
-            sharded.search(qv, qe, sp, sparse_tokens=ent)
-            launches += retr.last_launches + 1 + 1          # + mixture-weights kernel + cross-shard merge kernel
+            launches += step(pool[i % len(pool)])
         e1.record()
         barrier()
         if ncu_range:
@@ -332,6 +366,8 @@ def main():
             n = nv.lib().mfar_profile_collect(ctypes.addressof(buf), 256)
             kern_ms = [buf[i] for i in range(max(n, 0))]
             nv.lib().mfar_profile_enable(0)
+        if eager_kern_ms is not None:
+            kern_ms = eager_kern_ms
         if world > 1:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -438,7 +474,9 @@ def main():
             traffic = json.load(open(tpath)).get(f"{args.workload}|{Q}")
         roof.update({"traffic": traffic, "traffic_source": "ncu --set full capture, profiles/ncu_traffic.json" if traffic else None,
                      "kernel": kname,
-                     "kernel_ms": k_ms, "kernel_share_of_step": k_ms * len(kern_ms) / ms_total if ms_total else None,
+                     "kernel_ms": k_ms,
+                     "kernel_share_of_step": (k_ms * args.steps if args.graph else k_ms * len(kern_ms)) / ms_total
+                     if ms_total else None,
                      "algorithmic_bytes_per_launch": a_bytes, "algorithmic_flops_per_launch": a_flops,
                      "peak_source": peaks["source"] + (" (sustained: kernel timed inside a long step)" if not hbm_bound else " copy bandwidth")})
     else:
@@ -476,9 +514,12 @@ def main():
                     "path": "mfar_search_host (C ABI, pinned host buffers)" if world == 1 else
                             "pinned host -> device copies + sharded search + D2H of the merged top-k"},
             "sparse_stage": sparse_stage, "gpu_launches": launches, "exchange": exchange_kind, "clocks": clocks, "other_batches": extra, "setup_s": setup_s,
-            "kernel_impl": args.kernel,
+            "kernel_impl": args.kernel, "cuda_graph": bool(args.graph and world == 1),
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmfar_b200.so")
+LIB_PATH = os.environ.get("MFAR_LIB") or os.path.join(_HERE, "libmfar_b200.so")   # MFAR_LIB: instrumented builds
 
 F32, BF16, F16 = 0, 1, 2
 IMPL = {"auto": 0, "simt": 1, "tcgen05": 2, "tcgen05_qs": 3}

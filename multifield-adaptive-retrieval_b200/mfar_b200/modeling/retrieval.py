@@ -563,3 +563,70 @@ class MultiFieldRetriever:
         for qid, svals, rows in zip(query_ids, scores, ids):
             for sim, row in zip(svals, rows):
                 print(QRes(query_id=qid, doc_id=self.numeric_ids_to_keys[row], sim=sim), file=qres_output)
+
+
+class GraphedSearch:
+    """``MultiFieldRetriever.search`` for one fixed batch shape captured in a CUDA graph: the mixture-weights kernel,
+    the sparse pre-mix / BM25 plan + scatter, the fused scoring kernel and the merge replay as ONE graph launch.
+    For small shards (PRIME-2k, Q=64: the kernels take ~60 us, the 4-5 launches with their Python/ctypes calls ~110 us)
+    the step is launch-bound and the graph removes that; for corpus-sized shards it changes nothing.
+
+    Inputs are copied into static device buffers (``copy_`` accepts host or device tensors), outputs are the static
+    ``scores`` / ``ids`` tensors (valid until the next call).  BM25 token entries are padded to ``max_entries`` rows
+    with (-1, 0, 0), which the plan kernel skips.  The graph holds the retriever's mask / weight tensors as they were at
+    capture time: build a new GraphedSearch after ``mask_field``."""
+
+    def __init__(self, retriever: "MultiFieldRetriever", batch: int, sparse: str = "none", max_entries: int = 0,
+                 top_k: Optional[int] = None, sparse_dtype=torch.float16, sparse_ld: Optional[int] = None):
+        r = self.r = retriever
+        dev = r.device
+        self.k = top_k or r.top_k
+        self.Q = int(batch)
+        self.sparse_kind = sparse
+        dim = r.corpus.dim if r.corpus is not None else 1
+        self.q_vecs = torch.zeros((self.Q, dim), dtype=torch.bfloat16, device=dev) if r.corpus is not None else None
+        E = r.mixture.weight.shape[0] if r.mixture.query_cond else 0
+        self.q_emb = torch.zeros((self.Q, E), dtype=torch.float32, device=dev) if E else None
+        self.sparse = self.entries = None
+        if sparse == "dense":
+            ld = sparse_ld or _round_up(r.n_docs, 8)
+            self.sparse = torch.zeros((self.Q, r.n_sparse, ld), dtype=sparse_dtype, device=dev)
+        elif sparse == "bm25":
+            if r.bm25 is None or max_entries <= 0:
+                raise ValueError("sparse='bm25' needs a retriever with sparse_indices and max_entries > 0")
+            self.entries = torch.full((int(max_entries), 3), -1, dtype=torch.int32, device=dev)
+        elif sparse != "none":
+            raise ValueError("sparse must be 'none', 'dense' or 'bm25'")
+        if r.n_sparse and sparse == "none":
+            raise ValueError("retriever has sparse fields: pass sparse='dense' or 'bm25'")
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # warm-up: workspaces, attributes, tensor maps
+            for _ in range(2):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.scores, self.ids = self._run()
+        self.launches = r.last_launches + 1                # + mixture weights
+
+    def _run(self):
+        return self.r.search(self.q_vecs, self.q_emb, self.sparse, top_k=self.k, sparse_tokens=self.entries,
+                             batch=self.Q)
+
+    def __call__(self, q_vecs=None, q_emb=None, sparse=None, entries=None):
+        if self.q_vecs is not None:
+            self.q_vecs.copy_(q_vecs, non_blocking=True)
+        if self.q_emb is not None:
+            self.q_emb.copy_(q_emb if q_emb is not None else q_vecs, non_blocking=True)
+        if self.sparse is not None:
+            self.sparse[:, :, : sparse.shape[2]].copy_(sparse, non_blocking=True)
+        if self.entries is not None:
+            n = entries.shape[0]
+            if n > self.entries.shape[0]:
+                raise ValueError(f"{n} token entries exceed the captured capacity {self.entries.shape[0]}")
+            self.entries[:n].copy_(entries, non_blocking=True)
+            self.entries[n:, 0] = -1
+        self.graph.replay()
+        return self.scores, self.ids
