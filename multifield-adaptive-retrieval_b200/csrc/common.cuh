@@ -59,8 +59,8 @@ __host__ __device__ __forceinline__ uint32_t key_doc(uint64_t key) { return ~uin
 
 // Workspace carve-up shared by the scoring kernels and the merge.
 //   cand_keys [G][Qp][kCandCap] u64 | cand_thr [G][Qp] u64 | cand_cnt [G][Qp] i32 | err flag (256 B) |
-//   progress counters (kProgressInts i32) | gthr [Qp] u64 | gpool [Qp] u64 | gpub [Qp] i32
-//   (the whole tail is zeroed by the scoring-kernel launcher)
+//   progress counters (kProgressInts i32) | gthr [Qp] u64 | pool [G][Qp] u64
+//   (the tail from the progress counters on is zeroed by the scoring-kernel launcher)
 // gthr[q] = best admission threshold any CTA has established for query q (atomicMax of a k-th key).  The k-th key
 // of ANY subset of the shard is a lower bound of the shard's k-th key, so every CTA may filter with it: the
 // admitted-candidate count (and with it the list compactions) drops from k*ln(N_cta/k) per CTA to ~that in total.
@@ -71,8 +71,7 @@ struct TopkWorkspace {
   int* err;
   int* progress;
   unsigned long long* gthr;
-  unsigned long long* gpool;   // ~(min over CTAs of their rank-r key), r = ceil(k / #CTAs), see pooled_rank()
-  int* gpub;                   // how many CTAs have published into gpool[q]
+  unsigned long long* pool;    // [G][Qp]: latest rank-r key bound of each CTA's list, r = ceil(k / G) (0 = none yet)
   int workers;  // G
   int q_pad;    // Qp
 };
@@ -80,10 +79,12 @@ struct TopkWorkspace {
 
 inline size_t topk_workspace_bytes(int workers, int q_pad) {
   size_t n = size_t(workers) * q_pad;
-  return n * kCandCap * 8 + n * 8 + round_up(int(n * 4), 256) + 256 + kProgressInts * 4 + size_t(q_pad) * 20;
+  return n * kCandCap * 8 + n * 8 + round_up(int(n * 4), 256) + 256 + kProgressInts * 4 + size_t(q_pad) * 8 + n * 8;
 }
-// bytes of the zero-initialised tail (progress + gthr), starting at TopkWorkspace::progress
-inline size_t workspace_zero_bytes(int q_pad) { return size_t(kProgressInts) * 4 + size_t(q_pad) * 20; }
+// bytes of the zero-initialised tail (progress + gthr + pool), starting at TopkWorkspace::progress
+inline size_t workspace_zero_bytes(int workers, int q_pad) {
+  return size_t(kProgressInts) * 4 + size_t(q_pad) * 8 + size_t(workers) * q_pad * 8;
+}
 inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
   TopkWorkspace w;
   size_t n = size_t(workers) * q_pad;
@@ -94,8 +95,7 @@ inline TopkWorkspace carve_workspace(void* base, int workers, int q_pad) {
   w.err = reinterpret_cast<int*>(p);            p += 256;
   w.progress = reinterpret_cast<int*>(p);       p += kProgressInts * 4;
   w.gthr = reinterpret_cast<unsigned long long*>(p);   p += size_t(q_pad) * 8;
-  w.gpool = reinterpret_cast<unsigned long long*>(p);  p += size_t(q_pad) * 8;
-  w.gpub = reinterpret_cast<int*>(p);
+  w.pool = reinterpret_cast<unsigned long long*>(p);
   w.workers = workers;
   w.q_pad = q_pad;
   return w;
@@ -139,10 +139,36 @@ __device__ __forceinline__ void warp_sort256_desc(uint64_t (&v)[8], int lane) {
 
 // Pooled threshold.  If every one of the G CTAs scanning a query's shard holds at least r = ceil(k/G) keys >= x_g,
 // then min_g(x_g) has at least G*r >= k keys above it shard-wide: a valid admission threshold that is far tighter
-// than any single CTA's own k-th key early on (after the first compaction round it is roughly the k-th best of ALL
-// docs scanned so far by all CTAs, not of one CTA's slice), which removes most later compaction rounds.
-// Each CTA publishes the rank-r key of its sorted list once (first compaction); gpool holds ~min via atomicMax(~key).
+// than any single CTA's own k-th key (it tracks roughly the k-th best of ALL docs scanned so far by all CTAs, not of
+// one CTA's slice).  Every CTA re-publishes x_g = a lower bound of the rank-r key of its list at EVERY compaction
+// (pool[g][q], single writer, monotone), then takes the min over the G slots and raises the shared gthr[q] with it
+// (atomicMax of valid bounds stays a valid bound).  Readers keep reading just gthr[q].
 __host__ __device__ inline int pooled_rank(int k, int G) { return (k + G - 1) / G; }
+
+__device__ __forceinline__ unsigned long long ws_ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Whole warp: publish this CTA's bound for query q and return min over all G CTAs' bounds (0 while any is missing).
+__device__ __forceinline__ unsigned long long pool_publish_and_min(unsigned long long* pool, int G, int q_pad, int g,
+                                                                   int q, unsigned long long mine, int lane) {
+  if (lane == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(pool + (long long)g * q_pad + q), "l"(mine) : "memory");
+  unsigned long long m = mine;
+  for (int gg = lane; gg < G; gg += 32) {
+    if (gg != g) {
+      const unsigned long long v = ws_ld_relaxed_u64(pool + (long long)gg * q_pad + q);
+      m = v < m ? v : m;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+    m = v < m ? v : m;
+  }
+  return m;
+}
 
 // One warp compacts the candidate list of one (worker, query): keep the best k keys (sorted
 // descending), return the k-th key (new admission threshold).  `list` points at kCandCap slots
@@ -176,7 +202,7 @@ __device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, int count,
 constexpr int kSelectSlack = 24;
 
 __device__ __forceinline__ uint64_t warp_select_list(uint64_t* list, int count, int k, int max_keep, int lane,
-                                                     int* new_count) {
+                                                     int* new_count, int r, uint64_t* rank_r_bound) {
   // max_keep: the caller's list may hold at most this many keys after compaction (its overflow trigger level)
   const int slack = min(kSelectSlack, max_keep - k);
   uint64_t v[8];
@@ -207,7 +233,22 @@ __device__ __forceinline__ uint64_t warp_select_list(uint64_t* list, int count, 
   }
   if (c_lo > k + slack) {                               // a big tie group straddles rank k (or no slack): exact path
     *new_count = k;
-    return warp_compact_list(list, count, k, lane);
+    const uint64_t kth = warp_compact_list(list, count, k, lane);
+    __syncwarp();
+    *rank_r_bound = __ldcg(list + r - 1);               // sorted now: the exact rank-r key
+    return kth;
+  }
+  {                                                     // same search for rank r <= k on [lo, mx]: count(>= lo) >= k >= r
+    uint32_t lo2 = lo, up2 = mx;
+    while (lo2 < up2) {
+      const uint32_t mid = lo2 + ((up2 - lo2 + 1u) >> 1);
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c += (hi[j] >= mid) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= r) lo2 = mid; else up2 = mid - 1u;
+    }
+    *rank_r_bound = (uint64_t(lo2) << 32) - 1ull;       // >= r keys have score word >= lo2, i.e. key > this bound
   }
   int base = 0;
 #pragma unroll

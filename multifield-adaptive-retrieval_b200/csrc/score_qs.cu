@@ -282,7 +282,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     const float* my_base = p.base ? p.base + int64_t(q_valid ? qrow : 0) * p.base_ld : nullptr;
     uint64_t thr = 0ull;
     int cnt = 0;
-    bool published = false, pool_adopted = false;
+    bool published = false;
     const int refresh_mask = p.n_dense >= 8 ? 0 : (p.n_dense >= 4 ? 1 : (p.n_dense >= 2 ? 3 : 7));
     float acc[kQsDocs];
     int u = 0;
@@ -338,12 +338,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         // per ~8 MMA units (every half-tile when n_dense >= 8, every 8th for a single_ scorer)
         if (q_valid && (((2 * i + h) & refresh_mask) == 0)) {
           const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + qrow);
-          thr = gt > thr ? gt : thr;
-          if (!pool_adopted && ld_relaxed_s32(p.ws.gpub + qrow) == G) {   // every CTA of this query has published
-            const unsigned long long pt = ~ld_relaxed_u64(p.ws.gpool + qrow);
-            thr = pt > thr ? pt : thr;
-            pool_adopted = true;
-          }
+          thr = gt > thr ? gt : thr;                                     // incl. the pooled bound, common.cuh
         }
         if (q_valid && doc0 < p.n_docs) {
           const int64_t left = p.n_docs - doc0;
@@ -352,9 +347,10 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           // one float compare per doc rejects almost everything; the exact (score, id) key is only built for docs
           // whose score reaches the threshold's score (thr == 0: nothing established yet, admit all)
           const float thr_f = thr ? key_score(thr) : -INFINITY;
-          // ... and one compare per GROUP of 8 docs (max tree: 7 FMNMX + 1 FSETP instead of 8 FSETP + 8 branches)
-          // rejects almost every group once a threshold exists - with a single_ scorer this push phase runs after
-          // every MMA unit and is what paces the kernel.
+          // ... and one compare per GROUP of 8 docs (max tree: 3 FMNMX/FMNMX3 + 1 FSETP instead of 8 FSETP + 8
+          // branches) rejects almost every group once a threshold exists - with a single_ scorer this push phase runs
+          // after every MMA unit.  (A branch-free 64-bit pass mask was measured too: its 3 instructions per doc cost
+          // more than the 8 group branches it saves - single_ Q=512 8.2 ms vs 7.5 ms.)
 #pragma unroll
           for (int c0 = 0; c0 < kQsDocs; c0 += 8) {
             const float m = fmaxf(fmaxf(fmaxf(acc[c0], acc[c0 + 1]), fmaxf(acc[c0 + 2], acc[c0 + 3])),
@@ -383,21 +379,26 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
           __syncwarp();
           const bool first_l = __shfl_sync(0xffffffffu, int(published), l) == 0;
-          int cnt_new = p.k;                           // first round: exact sort (its rank-r key is published);
-          const uint64_t kth = first_l ? warp_compact_list(list_l, cnt_l, p.k, lane)   // later rounds: cheap select
-                                       : warp_select_list(list_l, cnt_l, p.k, kCandCap - kQsDocs, lane, &cnt_new);
+          int cnt_new = p.k;                           // first round: exact sort; later rounds: cheap select
+          const int r = pooled_rank(p.k, G);
+          uint64_t bound_r = 0ull;
+          uint64_t kth;
+          if (first_l) {
+            kth = warp_compact_list(list_l, cnt_l, p.k, lane);
+            __syncwarp();
+            bound_r = __ldcg(list_l + r - 1);
+          } else {
+            kth = warp_select_list(list_l, cnt_l, p.k, kCandCap - kQsDocs, lane, &cnt_new, r, &bound_r);
+          }
           __syncwarp();
+          const int qrow_l = __shfl_sync(0xffffffffu, qrow, l);
+          const unsigned long long pooled = pool_publish_and_min(p.ws.pool, G, p.ws.q_pad, g, qrow_l, bound_r, lane);
           if (lane == l) {
             thr = kth > thr ? kth : thr;
+            thr = pooled > thr ? pooled : thr;
             cnt = cnt_new;
+            published = true;
             atomicMax(p.ws.gthr + qrow, thr);
-            if (!published) {                          // first compaction of this list: publish its rank-r key
-              published = true;
-              const unsigned long long key_r = __ldcg(list_l + pooled_rank(p.k, G) - 1);
-              atomicMax(p.ws.gpool + qrow, ~key_r);
-              __threadfence();
-              atomicAdd(p.ws.gpub + qrow, 1);
-            }
           }
           __syncwarp();
         }
@@ -476,7 +477,7 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
     attr_set = true;
   }
   // lockstep counters of the query groups (producer warp) + shared per-query thresholds (epilogue)
-  MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.q_pad), st));
+  MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(q_tiles, workers);
   cfg.blockDim = dim3(kQsThreads);

@@ -52,15 +52,16 @@ template <int QP>
 __global__ void __launch_bounds__(kTcThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B resident][w_s][thr][cnt][barriers][tmem ptr]
+  // carve: [A stages][B resident][w_s][thr as float][thr][cnt][flags][barriers][tmem ptr]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + size_t(p.stages) * kABytes;
   const int b_chunk_bytes = QP * kChunkK * 2;
   float* w_s = reinterpret_cast<float*>(smem_b + size_t(p.k_chunks) * b_chunk_bytes);     // [n_dense][QP]
-  unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(w_s + size_t(p.n_dense) * QP);
+  float* s_thrf = w_s + size_t(p.n_dense) * QP;    // [QP] score of s_thr (float pre-filter), +inf for padding queries
+  unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(s_thrf + QP);
   int* s_cnt = reinterpret_cast<int*>(s_thr + QP);
-  int* s_flags = s_cnt + QP;                       // bit 0: published to gpool, bit 1: pooled threshold adopted
+  int* s_flags = s_cnt + QP;                       // bit 0: list has had its first (exact) compaction
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_flags + QP) + 7) & ~uintptr_t(7));
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + p.stages;           // [stages]
@@ -82,7 +83,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int f = i / QP, c = i % QP;
     w_s[i] = (c < nq) ? p.w[int64_t(q0 + c) * p.w_ld + f] : 0.f;
   }
-  if (threadIdx.x < QP) { s_thr[threadIdx.x] = 0ull; s_cnt[threadIdx.x] = 0; s_flags[threadIdx.x] = 0; }
+  if (threadIdx.x < QP) {
+    s_thr[threadIdx.x] = 0ull; s_cnt[threadIdx.x] = 0; s_flags[threadIdx.x] = 0;
+    s_thrf[threadIdx.x] = int(threadIdx.x) < nq ? -INFINITY : INFINITY;
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -169,13 +173,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       {                                              // adopt the best threshold any CTA found for these queries
         const int et0 = threadIdx.x - 64;
         if (et0 < nq) {
-          const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + q0 + et0);
-          if (gt > s_thr[et0]) s_thr[et0] = gt;
-          if (!(s_flags[et0] & 2) && ld_relaxed_s32(p.ws.gpub + q0 + et0) == int(gridDim.x)) {
-            const unsigned long long pt = ~ld_relaxed_u64(p.ws.gpool + q0 + et0);   // pooled threshold, common.cuh
-            if (pt > s_thr[et0]) s_thr[et0] = pt;
-            s_flags[et0] |= 2;
-          }
+          const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + q0 + et0);   // incl. the pooled bound, common.cuh
+          if (gt > s_thr[et0]) { s_thr[et0] = gt; s_thrf[et0] = key_score(gt); }
         }
         epi_bar_sync();
       }
@@ -217,13 +216,26 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // ---- tile done: filter, push
       if (doc_local < p.n_docs) {
         const uint32_t doc_id = uint32_t(p.doc_id_base + doc_local);
+        // Float pre-filter per GROUP of 8 queries: max_j(score[c0+j] - score of query c0+j's threshold) >= 0 decides
+        // with 8 FADD + 3 FMNMX3/FMNMX + 1 FSETP + 1 branch whether any of the 8 (doc, query) pairs can be admitted;
+        // the exact (score, id) key is only built inside live groups.  With one epilogue warp per scheduler every
+        // branch is a pipeline bubble: the former per-pair key compare (LDS + 2 ISETP + branch, x QP) made a single_
+        // scorer at Q=64 epilogue-bound (ncu: 0.56 of HBM peak, tensor pipe 10 % active).
 #pragma unroll
-        for (int c = 0; c < QP; ++c) {
-          if (c < nq) {
-            const uint64_t key = make_key(acc[c], doc_id);
-            if (key > s_thr[c]) {
-              const int pos = atomicAdd(&s_cnt[c], 1);
-              __stcg(p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap + pos, key);
+        for (int c0 = 0; c0 < QP; c0 += 8) {
+          const float4 ta = *reinterpret_cast<const float4*>(s_thrf + c0);
+          const float4 tb = *reinterpret_cast<const float4*>(s_thrf + c0 + 4);
+          const float m = fmaxf(fmaxf(fmaxf(acc[c0] - ta.x, acc[c0 + 1] - ta.y), fmaxf(acc[c0 + 2] - ta.z, acc[c0 + 3] - ta.w)),
+                                fmaxf(fmaxf(acc[c0 + 4] - tb.x, acc[c0 + 5] - tb.y), fmaxf(acc[c0 + 6] - tb.z, acc[c0 + 7] - tb.w)));
+          if (m >= 0.f) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c0 + j;
+              const uint64_t key = make_key(acc[c], doc_id);
+              if (key > s_thr[c] && c < nq) {
+                const int pos = atomicAdd(&s_cnt[c], 1);
+                __stcg(p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap + pos, key);
+              }
             }
           }
         }
@@ -233,21 +245,27 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int cnt = s_cnt[c];
         if (cnt > kCandCap - kTileDocs) {
           uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
-          int cnt_new = p.k;                           // first round: exact sort (its rank-r key is published);
-          const uint64_t kth = !(s_flags[c] & 1) ? warp_compact_list(list, cnt, p.k, lane)   // later: cheap select
-                                                 : warp_select_list(list, cnt, p.k, kCandCap - kTileDocs, lane, &cnt_new);
+          int cnt_new = p.k;                           // first round: exact sort; later rounds: cheap select
+          const int r = pooled_rank(p.k, int(gridDim.x));
+          uint64_t bound_r = 0ull;
+          uint64_t kth;
+          if (!(s_flags[c] & 1)) {
+            kth = warp_compact_list(list, cnt, p.k, lane);
+            __syncwarp();
+            bound_r = __ldcg(list + r - 1);
+          } else {
+            kth = warp_select_list(list, cnt, p.k, kCandCap - kTileDocs, lane, &cnt_new, r, &bound_r);
+          }
           __syncwarp();
+          const unsigned long long pooled = pool_publish_and_min(p.ws.pool, int(gridDim.x), p.ws.q_pad, g, q0 + c,
+                                                                 bound_r, lane);
           if (lane == 0) {
             if (kth > s_thr[c]) s_thr[c] = kth;
+            if (pooled > s_thr[c]) s_thr[c] = pooled;
+            s_thrf[c] = key_score(s_thr[c]);
             s_cnt[c] = cnt_new;
+            s_flags[c] |= 1;
             atomicMax(p.ws.gthr + q0 + c, s_thr[c]);
-            if (!(s_flags[c] & 1)) {                   // first compaction of this list: publish its rank-r key
-              s_flags[c] |= 1;
-              const unsigned long long key_r = __ldcg(list + pooled_rank(p.k, int(gridDim.x)) - 1);
-              atomicMax(p.ws.gpool + q0 + c, ~key_r);
-              __threadfence();
-              atomicAdd(p.ws.gpub + q0 + c, 1);
-            }
           }
         }
       }
@@ -286,7 +304,7 @@ void score_tc_geometry(int Q, int n_tiles, int* q_pad, int* q_tiles, int* worker
 
 static size_t tc_smem_bytes(int qp, int n_dense, int k_chunks, int stages) {
   return 1024 + size_t(stages) * kABytes + size_t(k_chunks) * qp * kChunkK * 2 + size_t(n_dense) * qp * 4 +
-         size_t(qp) * 16 + 8 + (2 * stages + 5) * 8 + 16;
+         size_t(qp) * 20 + 8 + (2 * stages + 5) * 8 + 16;
 }
 
 template <int QP>
@@ -315,7 +333,7 @@ static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
     MFAR_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
     attr_set = true;
   }
-  MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.q_pad), st));   // shared thresholds
+  MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));   // shared thresholds
   dim3 grid(workers, q_tiles);
   score_tc_kernel<QP><<<grid, kTcThreads, smem, st>>>(map_a, map_b, p);
   MFAR_CUDA_OK(cudaGetLastError());
