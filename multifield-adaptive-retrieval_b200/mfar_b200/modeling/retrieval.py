@@ -343,14 +343,21 @@ class MultiFieldRetriever:
     @torch.no_grad()
     def search_mask_sweep(self, q_vecs, masked_sets: Sequence[Sequence[int]], q_emb: Optional[torch.Tensor] = None,
                           sparse: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
-                          max_rows: int = 1024) -> Tuple[torch.Tensor, torch.Tensor]:
+                          max_rows: int = 1024, sparse_tokens=None) -> Tuple[torch.Tensor, torch.Tensor]:
         """All M maskings of ``mask_field`` evaluated as extra weight rows of ONE fused pass per chunk: the mask only
         multiplies the softmax weights (contrastive.py:686, no renormalisation), so masking m of query q is the
         pseudo-query (q, w[q] * mask_m).  Returns (scores [M,Q,k], ids [M,Q,k]).  Rows are processed in chunks of
-        at most ``max_rows`` pseudo-queries; dense sparse-score tensors are repeated per chunk."""
+        at most ``max_rows`` pseudo-queries; dense sparse-score tensors are repeated per chunk, BM25 token entries
+        (``sparse_tokens``, for a retriever with ``sparse_indices``) are replicated with shifted query rows."""
         k = top_k or self.top_k
         q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
-        Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
+        ent = self._bm25_entries(sparse_tokens) if sparse_tokens is not None else None
+        if q_bf16 is not None:
+            Q = q_bf16.shape[0]
+        elif sparse is not None:
+            Q = sparse.shape[0]
+        else:
+            Q = len(sparse_tokens[0])
         if self.mixture.query_cond:
             qe = q_emb if q_emb is not None else (q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs))
             qe = qe.to(self.device).float()
@@ -361,7 +368,7 @@ class MultiFieldRetriever:
         masks = torch.ones((M, self.num_fields), dtype=torch.float32, device=self.device)
         for m, idx in enumerate(masked_sets):
             masks[m, list(idx)] = 0
-        sp, code = self._check_sparse(sparse, Q)
+        sp, code = self._check_sparse(sparse, Q) if ent is None else (None, nv.F16)
         out_s = torch.empty((M, Q, k), dtype=torch.float32, device=self.device)
         out_i = torch.empty((M, Q, k), dtype=torch.int64, device=self.device)
         per_chunk = max(1, max_rows // Q)
@@ -371,7 +378,13 @@ class MultiFieldRetriever:
             w_rows = (w.unsqueeze(0) * masks[m0:m1].unsqueeze(1)).reshape(reps * Q, -1).contiguous()
             q_rows = q_bf16.repeat(reps, 1) if q_bf16 is not None else None
             sp_rows = sp.repeat(reps, 1, 1) if sp is not None else None
-            s, i, _ = self._score_topk(q_rows, w_rows, sp_rows, code, k, 0, self.n_dense, self.n_sparse)
+            ent_rows = None
+            if ent is not None:                                            # query-major order is kept: rep-major
+                ent_rows = ent.unsqueeze(0).repeat(reps, 1, 1)
+                ent_rows[:, :, 0] += (torch.arange(reps, device=self.device, dtype=torch.int32) * Q).view(reps, 1)
+                ent_rows = ent_rows.view(-1, 3).contiguous()
+            s, i, _ = self._score_topk(q_rows, w_rows, sp_rows, code, k, 0, self.n_dense, self.n_sparse,
+                                       bm25_entries=ent_rows)
             out_s[m0:m1] = s.view(reps, Q, k)
             out_i[m0:m1] = i.view(reps, Q, k)
         return out_s, out_i

@@ -243,3 +243,49 @@ def test_bm25s_sparse_index_api(tmp_path):
     back = BM25sSparseIndex.load(str(tmp_path / "ix"), device=DEV)
     assert back.keys == idx.keys
     np.testing.assert_array_equal(back.get_scores(q), got)
+
+
+def test_mask_sweep_with_device_bm25_equals_mask_field_loop():
+    DeviceBM25, MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    N, d, Fd, Fs, Q, V = 3000, 64, 2, 2, 5, 300
+    g = torch.Generator().manual_seed(21)
+    dense = [O.round_bf16(torch.randn(N, d, generator=g)) for _ in range(Fd)]
+    qv = O.round_bf16(torch.randn(Q, d, generator=g))
+    bm = [DeviceBM25(device=DEV).index(_corpus(80 + j, N, V, 9), vocab=V) for j in range(Fs)]
+    tokens = [_queries(90 + j, Q, V, 5) for j in range(Fs)]
+    layer = LinearWeights(d, Fd + Fs, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(0.05 * torch.randn(d, Fd + Fs, generator=g))
+    r = MultiFieldRetriever(PackedCorpus.from_fields(dense, DEV), layer.to(DEV), sparse_indices=bm)
+    sets = [[], [0], [3], [2, 3], [0, 1]]
+    ss, ii = r.search_mask_sweep(qv.to(DEV), sets, sparse_tokens=tokens, max_rows=12)   # 2 maskings per chunk
+    for m, idx in enumerate(sets):
+        r.mask_field(idx)
+        s, i = r.search(qv.to(DEV), qv.to(DEV), sparse_tokens=tokens)
+        assert torch.equal(ii[m], i)
+        torch.testing.assert_close(ss[m], s, rtol=2e-6, atol=1e-6)
+
+
+def test_empty_sparse_field_and_unknown_tokens_only():
+    """A field whose postings are empty for this shard (nnz = 0) and a batch whose tokens are all out of vocabulary."""
+    DeviceBM25, MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    N, d, V, Q = 1000, 64, 50, 3
+    g = torch.Generator().manual_seed(22)
+    dense = [O.round_bf16(torch.randn(N, d, generator=g))]
+    qv = O.round_bf16(torch.randn(Q, d, generator=g))
+    full = DeviceBM25(device=DEV).index([[1, 2, 3]] * 10 + [[4]] * (2 * N - 10), vocab=V)   # 2N docs
+    empty_here = full.shard(N, 2 * N).shard(0, N)                       # docs N..2N only contain token 4
+    assert empty_here.num_docs == N
+    layer = LinearWeights(d, 2, query_cond=True)
+    with torch.no_grad():
+        layer.weight.copy_(0.05 * torch.randn(d, 2, generator=g))
+    r = MultiFieldRetriever(PackedCorpus.from_fields(dense, DEV), layer.to(DEV), sparse_indices=[empty_here])
+    w = O.mixture_weights(qv, layer.weight.detach().cpu(), True)
+    ref0 = O.exhaustive_scores(qv, dense, torch.zeros(Q, 1, N), w)
+    for toks in ([[1, 2], [3], [1]], [[V + 3], [V + 9, V + 1], []]):    # tokens absent from this shard / from the vocabulary
+        s, i = r.search(qv.to(DEV), qv.to(DEV), sparse_tokens=[toks])
+        assert_topk_parity(s.cpu().numpy(), i.cpu().numpy(), ref0.numpy(), 100)
+    nothing = DeviceBM25.from_csc(np.zeros(0, np.float32), np.zeros(0, np.int32), np.zeros(V + 1, np.int64), N, device=DEV)
+    r2 = MultiFieldRetriever(PackedCorpus.from_fields(dense, DEV), layer.to(DEV), sparse_indices=[nothing])
+    s, i = r2.search(qv.to(DEV), qv.to(DEV), sparse_tokens=[[[1, 2], [3], [1]]])
+    assert_topk_parity(s.cpu().numpy(), i.cpu().numpy(), ref0.numpy(), 100)
