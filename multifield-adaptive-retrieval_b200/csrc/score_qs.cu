@@ -282,7 +282,6 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     const float* my_base = p.base ? p.base + int64_t(q_valid ? qrow : 0) * p.base_ld : nullptr;
     uint64_t thr = 0ull;
     int cnt = 0;
-    bool published = false;
     const int refresh_mask = p.n_dense >= 8 ? 0 : (p.n_dense >= 4 ? 1 : (p.n_dense >= 2 ? 3 : 7));
     float acc[kQsDocs];
     int u = 0;
@@ -378,18 +377,13 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
           uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
           __syncwarp();
-          const bool first_l = __shfl_sync(0xffffffffu, int(published), l) == 0;
-          int cnt_new = p.k;                           // first round: exact sort; later rounds: cheap select
+          // every round is a warp SELECT (binary search on the score word; it also yields the rank-r bound that is
+          // published) - the exact bitonic sort the first round used to run cost ~5x more, a fixed ~0.25 ms per launch
+          // (128 lists per CTA) that mid-size shards (MAG 700k docs, the 8-GPU shards) paid in full
+          int cnt_new = p.k;
           const int r = pooled_rank(p.k, G);
           uint64_t bound_r = 0ull;
-          uint64_t kth;
-          if (first_l) {
-            kth = warp_compact_list(list_l, cnt_l, p.k, lane);
-            __syncwarp();
-            bound_r = __ldcg(list_l + r - 1);
-          } else {
-            kth = warp_select_list(list_l, cnt_l, p.k, kCandCap - kQsDocs, lane, &cnt_new, r, &bound_r);
-          }
+          const uint64_t kth = warp_select_list(list_l, cnt_l, p.k, kCandCap - kQsDocs, lane, &cnt_new, r, &bound_r);
           __syncwarp();
           const int qrow_l = __shfl_sync(0xffffffffu, qrow, l);
           const unsigned long long pooled = pool_publish_and_min(p.ws.pool, G, p.ws.q_pad, g, qrow_l, bound_r, lane);
@@ -397,7 +391,6 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
             thr = kth > thr ? kth : thr;
             thr = pooled > thr ? pooled : thr;
             cnt = cnt_new;
-            published = true;
             atomicMax(p.ws.gthr + qrow, thr);
           }
           __syncwarp();

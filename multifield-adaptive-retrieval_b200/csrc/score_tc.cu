@@ -61,7 +61,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   float* s_thrf = w_s + size_t(p.n_dense) * QP;    // [QP] score of s_thr (float pre-filter), +inf for padding queries
   unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(s_thrf + QP);
   int* s_cnt = reinterpret_cast<int*>(s_thr + QP);
-  int* s_flags = s_cnt + QP;                       // bit 0: list has had its first (exact) compaction
+  int* s_flags = s_cnt + QP;                       // reserved (keeps the shared-memory layout)
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_flags + QP) + 7) & ~uintptr_t(7));
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + p.stages;           // [stages]
@@ -245,17 +245,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int cnt = s_cnt[c];
         if (cnt > kCandCap - kTileDocs) {
           uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
-          int cnt_new = p.k;                           // first round: exact sort; later rounds: cheap select
+          int cnt_new = p.k;                           // every round: warp select (see score_qs.cu)
           const int r = pooled_rank(p.k, int(gridDim.x));
           uint64_t bound_r = 0ull;
-          uint64_t kth;
-          if (!(s_flags[c] & 1)) {
-            kth = warp_compact_list(list, cnt, p.k, lane);
-            __syncwarp();
-            bound_r = __ldcg(list + r - 1);
-          } else {
-            kth = warp_select_list(list, cnt, p.k, kCandCap - kTileDocs, lane, &cnt_new, r, &bound_r);
-          }
+          const uint64_t kth = warp_select_list(list, cnt, p.k, kCandCap - kTileDocs, lane, &cnt_new, r, &bound_r);
           __syncwarp();
           const unsigned long long pooled = pool_publish_and_min(p.ws.pool, int(gridDim.x), p.ws.q_pad, g, q0 + c,
                                                                  bound_r, lane);
@@ -264,7 +257,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (pooled > s_thr[c]) s_thr[c] = pooled;
             s_thrf[c] = key_score(s_thr[c]);
             s_cnt[c] = cnt_new;
-            s_flags[c] |= 1;
             atomicMax(p.ws.gthr + q0 + c, s_thr[c]);
           }
         }
