@@ -36,6 +36,7 @@ struct Geometry {
   int q_pad;      // per tile (tc, qs) or total (simt)
   int q_pad_total;
   int cg;         // qs: CTAs per MMA group (1 or 2)
+  int lists;      // candidate lists per query the scoring kernel fills (workers, or 2 x workers: qs single-field)
 };
 
 constexpr int kQsMinBatch = 65;   // AUTO: batches above 64 queries take the query-stationary kernel
@@ -52,6 +53,8 @@ static Geometry resolve_geometry(const ScoreArgs& a, int impl) {
     score_qs_geometry(a.Q, a.n_tiles, &g.q_tiles, &g.workers, &g.cg);
     g.q_pad = 128;
     g.q_pad_total = g.q_pad * g.q_tiles;
+    g.lists = g.workers * score_qs_lists_per_worker(a.n_dense, g.cg);
+    return g;
   } else if (impl == MFAR_IMPL_TCGEN05) {
     score_tc_geometry(a.Q, a.n_tiles, &g.q_pad, &g.q_tiles, &g.workers);
     g.q_pad_total = g.q_pad * g.q_tiles;
@@ -60,6 +63,7 @@ static Geometry resolve_geometry(const ScoreArgs& a, int impl) {
     g.q_tiles = 1;
     g.q_pad_total = g.q_pad;
   }
+  g.lists = g.workers;
   return g;
 }
 
@@ -144,7 +148,7 @@ size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_spars
   {
     int qt, w, cg;
     score_qs_geometry(Q, std::max(n_tiles, 1), &qt, &w, &cg);
-    best = std::max(best, topk_workspace_bytes(w, qt * 128));
+    best = std::max(best, topk_workspace_bytes(2 * w, qt * 128));   // single-field scorers keep 2 lists per CTA
   }
   size_t total = align_up(best, 256);
   if (n_sparse > 0) total += align_up(size_t(Q) * size_t(align_up(size_t(n_docs), kTileDocs)) * 4, 256);
@@ -207,7 +211,7 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   if (impl == MFAR_IMPL_TCGEN05_QS && !score_qs_supported(a)) return MFAR_ERR_SHAPE;
   const Geometry g = resolve_geometry(a, impl);
 
-  const size_t ws_topk = align_up(topk_workspace_bytes(g.workers, g.q_pad_total), 256);
+  const size_t ws_topk = align_up(topk_workspace_bytes(g.lists, g.q_pad_total), 256);
   const int64_t base_ld = int64_t(align_up(size_t(n_docs), kTileDocs));   // tile-wide vector reads stay in bounds
   const size_t ws_base = n_sparse > 0 ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
   const size_t ws_plan = (n_sparse > 0 && sp.kind == 3) ? bm25_plan_bytes(sp.n_entries) : 0;
@@ -256,8 +260,8 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   if (rc) return rc;
   if (prof) { MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][1], st)); ++g_prof_n; }
   ++t_last_launches;
-  TopkWorkspace ws = carve_workspace(workspace, g.workers, g.q_pad_total);
-  rc = launch_merge(ws.cand_keys, ws.cand_cnt, ws.cand_thr, g.workers, g.q_pad_total, kCandCap, Q, k, out_keys,
+  TopkWorkspace ws = carve_workspace(workspace, g.lists, g.q_pad_total);
+  rc = launch_merge(ws.cand_keys, ws.cand_cnt, ws.cand_thr, g.lists, g.q_pad_total, kCandCap, Q, k, out_keys,
                     out_scores, out_ids, st);
   if (rc) return rc;
   ++t_last_launches;

@@ -86,6 +86,8 @@ int launch_score_tc(const ScoreArgs& a, void* ws_base, int workers, int q_tiles,
 int launch_score_qs(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int cg, cudaStream_t st);
 bool score_qs_supported(const ScoreArgs& a);
 void score_qs_geometry(int Q, int n_tiles, int* q_tiles, int* workers, int* cg);
+// candidate lists per (worker CTA, query): 2 for a single-field scorer in CTA-pair mode (two epilogue sets), else 1
+int score_qs_lists_per_worker(int n_dense, int cg);
 // Shape envelope of the tcgen05 path.
 bool score_tc_supported(const ScoreArgs& a);
 // geometry chosen for (Q): q_pad per tile, number of q tiles, workers

@@ -22,7 +22,10 @@
 //
 // Warp roles (224 threads, 1 CTA / SM, persistent over doc tiles): warp 0 TMA producer, warp 1 TMEM
 // allocator + MMA issuer for even units, warp 6 MMA issuer for odd units (leader CTA only when CG = 2),
-// warps 2..5 epilogue.
+// warps 2..5 epilogue.  ES = 2 (single-field scorers): a SECOND epilogue set, warps 7..10 (352 threads).  With one
+// field every MMA unit ends in a push phase; one set is busy ~1.8k cycles per unit against 1.5k cycles of tensor time
+// and the issuers wait on the accumulator hand-back.  Set s owns accumulator buffer s, i.e. the units of half-tile s
+// of every tile, with its own candidate lists (list index g*ES + s), so each set has two unit times per unit.
 // grid = (q_tiles, workers): CTAs with the same blockIdx.y walk the same doc tiles for different query
 // tiles (adjacent in launch order -> co-resident in time, so re-reads hit L2).
 #include <cuda.h>
@@ -33,7 +36,9 @@
 
 namespace mfar {
 
-constexpr int kQsThreads = 224;
+constexpr int kQsThreads = 224;   // ES = 1; ES = 2 adds 4 epilogue warps
+constexpr int kQsEpiBWarp = 7;    // first warp of the second epilogue set
+__host__ __device__ constexpr int qs_threads(int es) { return kQsThreads + (es - 1) * 128; }
 constexpr int kQsIssuerBWarp = 6;   // second MMA-issuing warp (odd units)
 constexpr int kQsQ = 128;        // queries per CTA (TMEM lanes)
 constexpr int kQsDocs = 64;      // docs per unit (UMMA N)
@@ -76,8 +81,8 @@ __device__ __forceinline__ void qs_issue_stage(uint32_t d_tmem, uint32_t a0, uin
   }
 }
 
-template <int CG>
-__global__ void __launch_bounds__(kQsThreads, 1)
+template <int CG, int ES>
+__global__ void __launch_bounds__(qs_threads(ES), 1)
 score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
   constexpr int kRowsPerCta = kQsDocs / CG;               // doc rows this CTA loads per stage
   constexpr int kChunkBytes = kRowsPerCta * kChunkK * 2;  // one [rows x 64] K-major block: 8 KB (CG=1) / 4 KB (CG=2)
@@ -107,7 +112,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
   int* err = p.ws.err;
 
   // ---- one-time setup
-  for (int i = threadIdx.x; i < p.n_dense * kQsQ; i += kQsThreads) {
+  for (int i = threadIdx.x; i < p.n_dense * kQsQ; i += qs_threads(ES)) {
     const int f = i / kQsQ, c = i % kQsQ;
     w_s[i] = (q0 + c < p.Q) ? p.w[int64_t(q0 + c) * p.w_ld + f] : 0.f;
   }
@@ -278,7 +283,10 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     const int qloc = lane_grp * 32 + lane;
     const int qrow = q0 + qloc;
     const bool q_valid = qrow < p.Q;
-    uint64_t* my_list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + qrow) * kCandCap;
+    const int eset = (ES == 2 && warp >= kQsEpiBWarp) ? 1 : 0;     // epilogue set = accumulator buffer it drains
+    const int gl = g * ES + eset;                                  // candidate-list owner index (ES lists per CTA)
+    const int GL = G * ES;
+    uint64_t* my_list = p.ws.cand_keys + (int64_t(gl) * p.ws.q_pad + qrow) * kCandCap;
     const float* my_base = p.base ? p.base + int64_t(q_valid ? qrow : 0) * p.base_ld : nullptr;
     uint64_t thr = 0ull;
     int cnt = 0;
@@ -292,9 +300,11 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
 #else
 #define QS_ETICK(acc_)
 #endif
+    int n_push = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int t = g + i * G;
-      for (int h = 0; h < 2; ++h) {
+      for (int h = (ES == 2 ? eset : 0); h < (ES == 2 ? eset + 1 : 2); ++h) {
+        if (ES == 2) u = 2 * i + h;                              // single field: unit index == half-tile index
         const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
         // accumulators start from the pre-mixed sparse term (16 x 16-byte loads per query row, issued ahead of the
         // wait for the half-tile's first accumulator; base_ld is a multiple of 128, so the row read stays in bounds)
@@ -335,7 +345,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         // ---- 64 docs scored under every field: threshold filter, push
         // adopt the best threshold any CTA found for this query - an L2 round trip, so not more often than once
         // per ~8 MMA units (every half-tile when n_dense >= 8, every 8th for a single_ scorer)
-        if (q_valid && (((2 * i + h) & refresh_mask) == 0)) {
+        if (q_valid && ((n_push++ & refresh_mask) == 0)) {
           const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + qrow);
           thr = gt > thr ? gt : thr;                                     // incl. the pooled bound, common.cuh
         }
@@ -381,12 +391,12 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           // published) - the exact bitonic sort the first round used to run cost ~5x more, a fixed ~0.25 ms per launch
           // (128 lists per CTA) that mid-size shards (MAG 700k docs, the 8-GPU shards) paid in full
           int cnt_new = p.k;
-          const int r = pooled_rank(p.k, G);
+          const int r = pooled_rank(p.k, GL);
           uint64_t bound_r = 0ull;
           const uint64_t kth = warp_select_list(list_l, cnt_l, p.k, kCandCap - kQsDocs, lane, &cnt_new, r, &bound_r);
           __syncwarp();
           const int qrow_l = __shfl_sync(0xffffffffu, qrow, l);
-          const unsigned long long pooled = pool_publish_and_min(p.ws.pool, G, p.ws.q_pad, g, qrow_l, bound_r, lane);
+          const unsigned long long pooled = pool_publish_and_min(p.ws.pool, GL, p.ws.q_pad, gl, qrow_l, bound_r, lane);
           if (lane == l) {
             thr = kth > thr ? kth : thr;
             thr = pooled > thr ? pooled : thr;
@@ -404,8 +414,8 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
              warp, units, e_wait / 1000, e_drain / 1000, e_push / 1000, e_compact / 1000, n_compact);
 #endif
     if (q_valid) {
-      p.ws.cand_cnt[int64_t(g) * p.ws.q_pad + qrow] = cnt;
-      p.ws.cand_thr[int64_t(g) * p.ws.q_pad + qrow] = thr;
+      p.ws.cand_cnt[int64_t(gl) * p.ws.q_pad + qrow] = cnt;
+      p.ws.cand_thr[int64_t(gl) * p.ws.q_pad + qrow] = thr;
     }
   }
 
@@ -439,7 +449,11 @@ static size_t qs_smem_bytes(int n_dense, int stages, int stage_bytes) {
   return 1024 + size_t(stages) * stage_bytes + size_t(n_dense) * kQsQ * 4 + (2 * stages + 4) * 8 + 16;
 }
 
-template <int CG>
+// two epilogue sets only where the epilogue is the bound: single-field scorers in CTA-pair mode (Q > 128); at
+// Q <= 128 the kernel is HBM-bound and the extra warps measured ~3 % slower
+int score_qs_lists_per_worker(int n_dense, int cg) { return (n_dense == 1 && cg == 2) ? 2 : 1; }
+
+template <int CG, int ES>
 static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, cudaStream_t st) {
   constexpr int kChunkBytes = (kQsDocs / CG) * kChunkK * 2;
   QsParams p;
@@ -447,7 +461,7 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   p.n_dense = a.n_dense; p.k_chunks = a.dim / kChunkK; p.q_vecs = static_cast<const __nv_bfloat16*>(a.q_vecs);
   p.dim = a.dim; p.Q = a.Q; p.w = a.w; p.w_ld = a.w_ld; p.base = a.base; p.base_ld = a.base_ld;
   p.doc_id_base = a.doc_id_base; p.k = a.k;
-  p.ws = carve_workspace(ws_base, workers, q_tiles * kQsQ);
+  p.ws = carve_workspace(ws_base, workers * ES, q_tiles * kQsQ);   // ES candidate lists per (CTA, query)
   const size_t smem_cap = 227 * 1024;
   int kc = 1;                                       // largest divisor of k_chunks with a stage <= 48 KB
   for (int d = 1; d <= p.k_chunks; ++d)
@@ -466,14 +480,15 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   if (rc) return rc;
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    MFAR_CUDA_OK(cudaFuncSetAttribute(score_qs_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+    MFAR_CUDA_OK(cudaFuncSetAttribute(score_qs_kernel<CG, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(smem_cap)));
     attr_set = true;
   }
   // lockstep counters of the query groups (producer warp) + shared per-query thresholds (epilogue)
   MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(q_tiles, workers);
-  cfg.blockDim = dim3(kQsThreads);
+  cfg.blockDim = dim3(qs_threads(ES));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -481,14 +496,15 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MFAR_CUDA_OK(cudaLaunchKernelEx(&cfg, score_qs_kernel<CG>, map_b, p));
+  MFAR_CUDA_OK(cudaLaunchKernelEx(&cfg, score_qs_kernel<CG, ES>, map_b, p));
   return MFAR_OK;
 }
 
 int launch_score_qs(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int cg, cudaStream_t st) {
   if (!score_qs_supported(a)) return MFAR_ERR_SHAPE;
-  if (cg == 2) return launch_qs_impl<2>(a, ws_base, workers, q_tiles, st);
-  return launch_qs_impl<1>(a, ws_base, workers, q_tiles, st);
+  if (score_qs_lists_per_worker(a.n_dense, cg) == 2) return launch_qs_impl<2, 2>(a, ws_base, workers, q_tiles, st);
+  if (cg == 2) return launch_qs_impl<2, 1>(a, ws_base, workers, q_tiles, st);
+  return launch_qs_impl<1, 1>(a, ws_base, workers, q_tiles, st);
 }
 
 }  // namespace mfar
