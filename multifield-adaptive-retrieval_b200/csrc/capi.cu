@@ -37,12 +37,24 @@ struct Geometry {
   int q_pad_total;
   int cg;         // qs: CTAs per MMA group (1 or 2)
   int lists;      // candidate lists per query the scoring kernel fills (workers, or 2 x workers: qs single-field)
+  long long seg_docs;   // rows kernel: docs per segment
 };
+
+constexpr int kImplRows = 100;    // internal: sparse-only scorers (no dense field) -> streaming top-k of the base rows
 
 constexpr int kQsMinBatch = 65;   // AUTO: batches above 64 queries take the query-stationary kernel
 
 static Geometry resolve_geometry(const ScoreArgs& a, int impl) {
   Geometry g{};
+  if (a.n_dense == 0) {                                        // every impl request: there is nothing to contract
+    g.impl = kImplRows;
+    g.cg = 1;
+    g.q_tiles = 1;
+    topk_rows_geometry(a.Q, a.n_docs, &g.workers, &g.seg_docs);
+    g.q_pad = g.q_pad_total = round_up(a.Q, 4);
+    g.lists = g.workers;
+    return g;
+  }
   if (impl == MFAR_IMPL_AUTO) {
     if (a.Q >= kQsMinBatch && score_qs_supported(a)) impl = MFAR_IMPL_TCGEN05_QS;
     else impl = score_tc_supported(a) ? MFAR_IMPL_TCGEN05 : MFAR_IMPL_SIMT;
@@ -145,6 +157,11 @@ size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_spars
     score_simt_geometry(Q, std::max(n_tiles, 1), &qp, &w);
     best = std::max(best, topk_workspace_bytes(w, qp));
   }
+  if (n_sparse > 0) {
+    int segs; long long per;
+    topk_rows_geometry(Q, std::max<int64_t>(n_docs, 1), &segs, &per);
+    best = std::max(best, topk_workspace_bytes(segs, round_up(Q, 4)));
+  }
   {
     int qt, w, cg;
     score_qs_geometry(Q, std::max(n_tiles, 1), &qt, &w, &cg);
@@ -207,8 +224,8 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   a.corpus = corpus; a.n_docs = n_docs; a.n_tiles = int((n_docs + kTileDocs - 1) / kTileDocs);
   a.corpus_fields = corpus_fields; a.field_begin = field_begin; a.n_dense = n_dense; a.dim = dim;
   a.q_vecs = q_vecs; a.Q = Q; a.w = w; a.w_ld = n_dense + n_sparse; a.doc_id_base = doc_id_base; a.k = k;
-  if (impl == MFAR_IMPL_TCGEN05 && !score_tc_supported(a)) return MFAR_ERR_SHAPE;
-  if (impl == MFAR_IMPL_TCGEN05_QS && !score_qs_supported(a)) return MFAR_ERR_SHAPE;
+  if (n_dense > 0 && impl == MFAR_IMPL_TCGEN05 && !score_tc_supported(a)) return MFAR_ERR_SHAPE;
+  if (n_dense > 0 && impl == MFAR_IMPL_TCGEN05_QS && !score_qs_supported(a)) return MFAR_ERR_SHAPE;
   const Geometry g = resolve_geometry(a, impl);
 
   const size_t ws_topk = align_up(topk_workspace_bytes(g.lists, g.q_pad_total), 256);
@@ -251,7 +268,9 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   int rc;
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][0], st));
-  if (g.impl == MFAR_IMPL_TCGEN05_QS)
+  if (g.impl == kImplRows)
+    rc = launch_topk_rows(a, workspace, g.workers, g.seg_docs, st);
+  else if (g.impl == MFAR_IMPL_TCGEN05_QS)
     rc = launch_score_qs(a, workspace, g.workers, g.q_tiles, g.cg, st);
   else if (g.impl == MFAR_IMPL_TCGEN05)
     rc = launch_score_tc(a, workspace, g.workers, g.q_tiles, g.q_pad, st);
@@ -260,6 +279,7 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   if (rc) return rc;
   if (prof) { MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][1], st)); ++g_prof_n; }
   ++t_last_launches;
+  if (g.impl == kImplRows && n_docs >= 4096) ++t_last_launches;   // + the threshold-seed kernel
   TopkWorkspace ws = carve_workspace(workspace, g.lists, g.q_pad_total);
   rc = launch_merge(ws.cand_keys, ws.cand_cnt, ws.cand_thr, g.lists, g.q_pad_total, kCandCap, Q, k, out_keys,
                     out_scores, out_ids, st);

@@ -88,6 +88,9 @@ bool score_qs_supported(const ScoreArgs& a);
 void score_qs_geometry(int Q, int n_tiles, int* q_tiles, int* workers, int* cg);
 // candidate lists per (worker CTA, query): 2 for a single-field scorer in CTA-pair mode (two epilogue sets), else 1
 int score_qs_lists_per_worker(int n_dense, int cg);
+// Streaming top-k of the pre-mixed fp32 score rows (sparse-only scorers: no dense field).
+void topk_rows_geometry(int Q, long long n_docs, int* segments, long long* seg_docs);
+int launch_topk_rows(const ScoreArgs& a, void* ws_base, int segments, long long seg_docs, cudaStream_t st);
 // Shape envelope of the tcgen05 path.
 bool score_tc_supported(const ScoreArgs& a);
 // geometry chosen for (Q): q_pad per tile, number of q tiles, workers

@@ -19,6 +19,9 @@ SHAPES = {
     "amazon_full": (957192, 8, 8),
     "scale_10m_all": (10_000_000, 8, 0),
     "scale_10m_single": (10_000_000, 1, 0),
+    # sparse-only scorers (all_sparse field sets): no dense contraction, the pass is BM25 + streaming top-k
+    "amazon_sparse": (957192, 0, 8),
+    "prime_sparse": (129375, 0, 22),
 }
 
 
