@@ -133,7 +133,9 @@ SHAPES = [
     (22, 1500, 768, 5, 0, 1, True, 100),        # MAG-shaped, batch 1
     (23, 1111, 768, 8, 8, 3, True, 100),        # Amazon-shaped hybrid, ragged N
     (24, 900, 768, 1, 0, 5, False, 100),        # single_dense, static weights
-    (25, 700, 768, 0, 4, 6, False, 50),         # sparse only
+    (25, 700, 768, 0, 4, 6, False, 50),         # sparse only: streaming top-k of the pre-mixed rows (topk_rows.cu)
+    (32, 70000, 64, 0, 3, 9, True, 100),        # sparse only, seeded thresholds, several segments per row, ragged tail
+    (33, 4097, 64, 0, 1, 130, False, 128),      # sparse only, k = 128, just above the seeding size, N % 4 == 1
     (26, 3000, 768, 3, 2, 70, True, 100),       # Q > 64: two query tiles on the tcgen05 path
     (27, 129, 64, 2, 1, 17, True, 100),         # 2 tiles, the second with a single doc
     (28, 128, 128, 4, 0, 33, True, 128),        # k = 128 = N (everything returned)
@@ -148,7 +150,7 @@ SHAPES = [
 def test_exhaustive_search_vs_oracle(shape, impl):
     seed, N, d, Fd, Fs, Q, qc, k = shape
     if impl != "simt" and Fd == 0:
-        pytest.skip("sparse-only batches have no dense contraction: SIMT path by design")
+        pytest.skip("sparse-only batches have no dense contraction: every impl request runs topk_rows.cu")
     fields, q, sp, W = synth(seed, N, d, Fd, Fs, Q, qc)
     r = build(fields, W, qc, Fs, k, impl=impl, n_docs=N)
     mask = torch.ones(Fd + Fs, 1)
