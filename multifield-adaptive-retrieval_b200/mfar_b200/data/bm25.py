@@ -15,7 +15,7 @@ import ctypes
 import json
 import os
 import re
-from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch

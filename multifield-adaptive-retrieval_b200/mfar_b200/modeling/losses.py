@@ -12,7 +12,7 @@ cross-GPU gather are the same few torch / torch.distributed calls the reference 
 from __future__ import annotations
 
 import pickle
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
