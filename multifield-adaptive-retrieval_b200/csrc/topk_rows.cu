@@ -35,18 +35,24 @@ topk_rows_seed_kernel(const float* __restrict__ base, long long base_ld, long lo
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float* row = base + (long long)q * base_ld;
   uint32_t hi[kSeedPerThread];
+  const long long last_vec = ((n_docs - 1) / 4) * 4;       // base_ld is a multiple of 128: this 16-byte read is in bounds
 #pragma unroll
-  for (int i = 0; i < kSeedPerThread; ++i) {
-    const long long d = ((long long)i * kSeedThreads + tid) * 4;
-    float m = -INFINITY;
-    if (d < n_docs) {                                     // base_ld is a multiple of 128: the 16-byte read is in bounds
-      const float4 v = __ldg(reinterpret_cast<const float4*>(row + d));
-      m = v.x;
-      if (d + 1 < n_docs) m = fmaxf(m, v.y);
-      if (d + 2 < n_docs) m = fmaxf(m, v.z);
-      if (d + 3 < n_docs) m = fmaxf(m, v.w);
+  for (int i0 = 0; i0 < kSeedPerThread; i0 += 8) {         // 8 unconditional loads in flight, then the masking
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long d = ((long long)(i0 + j) * kSeedThreads + tid) * 4;
+      v[j] = __ldg(reinterpret_cast<const float4*>(row + (d < n_docs ? d : last_vec)));
     }
-    hi[i] = float_to_ordered(m);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long long d = ((long long)(i0 + j) * kSeedThreads + tid) * 4;
+      float m = d < n_docs ? v[j].x : -INFINITY;
+      m = d + 1 < n_docs ? fmaxf(m, v[j].y) : m;
+      m = d + 2 < n_docs ? fmaxf(m, v[j].z) : m;
+      m = d + 3 < n_docs ? fmaxf(m, v[j].w) : m;
+      hi[i0 + j] = float_to_ordered(m);
+    }
   }
   uint32_t lo = 0u, up = 0xFFFFFFFFu;                     // largest T with count(hi >= T) >= k
   while (lo < up) {
