@@ -238,3 +238,26 @@ def test_training_scorer_refuses_cpu_tensors_and_bad_layouts():
     assert lib.mfar_field_components_fwd(fake, 2, 8, fake, 4, 2, 1, 16, 8, 0, 0.0, fake, None) == 1
     assert lib.mfar_field_components_bwd(fake, 2, 8, fake, 4, 2, 1, 16, 8, 0, 1.0, fake, None, None, None) == 1
     assert lib.mfar_mixture_bwd(fake, fake, fake, fake, 3, fake, 2, 4, 8, 2, 1, None, fake, None, fake, None) == 2
+
+
+def test_header_is_valid_c_and_links_against_the_library(tmp_path):
+    """include/mfar_b200.h must be consumable from plain C (the drop-in boundary is a C ABI): compile a C translation
+    unit that takes the address of every declared entry point, link it against the .so, run it."""
+    import shutil
+    import subprocess
+    from mfar_b200 import _native as nv
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    header = open(os.path.join(ROOT, "include", "mfar_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(mfar_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S))))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mfar_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t fns[] = {\n' +
+                   "".join(f"    (fn_t)&{n},\n" for n in names) +
+                   '  };\n  if (mfar_abi_version() != MFAR_ABI_VERSION) return 2;\n'
+                   '  printf("%d %s\\n", (int)(sizeof fns / sizeof fns[0]), mfar_status_string(MFAR_ERR_ARCH));\n  return 0;\n}\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(nv.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", libdir, "-l:libmfar_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(" ", 1)
+    assert int(out[0]) == len(names) == len(nv.PROTOTYPES) and "sm_100" in out[1]
