@@ -109,10 +109,15 @@ class DeviceBM25:
 
     def _set(self, data, indices, indptr, num_docs: int, doc_base: int = 0) -> "DeviceBM25":
         dev = self.device
+
+        def dev_tensor(a, dtype):
+            if isinstance(a, np.ndarray) and not a.flags.writeable:    # np.load(mmap_mode="r"): copy before wrapping
+                a = np.array(a)
+            return torch.as_tensor(a).to(dev, dtype).contiguous()
         self.scores = {
-            "data": torch.as_tensor(data).to(dev, torch.float32).contiguous(),
-            "indices": torch.as_tensor(indices).to(dev, torch.int32).contiguous(),
-            "indptr": torch.as_tensor(indptr).to(dev, torch.int64).contiguous(),
+            "data": dev_tensor(data, torch.float32),
+            "indices": dev_tensor(indices, torch.int32),
+            "indptr": dev_tensor(indptr, torch.int64),
             "num_docs": int(num_docs),
         }
         self.doc_base = int(doc_base)
