@@ -142,6 +142,9 @@ SHAPES = [
     (29, 5000, 256, 2, 0, 130, True, 10),       # three query tiles
     (30, 4000, 768, 3, 1, 200, True, 100),      # large batch, hybrid: CTA-pair query-stationary path under auto
     (31, 2500, 768, 2, 0, 300, False, 100),     # 3 query tiles of 128 -> padded to 2 pairs
+    (34, 6000, 768, 1, 0, 300, True, 100),      # single_ scorer, CTA pairs: two epilogue sets (score_qs_kernel<2,2>)
+    (35, 3001, 256, 1, 2, 257, False, 100),     # single dense + 2 sparse fields, pairs + sparse base, ragged last tile
+    (36, 700, 128, 1, 0, 129, True, 128),       # single field, k = 128, Q just above one query tile
 ]
 
 
@@ -215,6 +218,30 @@ def test_query_stationary_agrees_with_doc_stationary_at_scale():
     assert all(len(set(row.tolist())) == k for row in i2.cpu())
     torch.testing.assert_close(s1, s2, rtol=2e-5, atol=1e-4)
     assert (i1 == i2).float().mean().item() > 0.98
+
+
+def test_single_field_two_epilogue_sets_agree_with_doc_stationary_at_scale():
+    """single_ scorer at Q=384 (CTA pairs, two epilogue sets with their own candidate lists) vs the doc-stationary
+    kernel over a corpus the oracle would take minutes for; also Q=1024 against itself split into two batches."""
+    MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    from mfar_b200 import synth as S
+    N, d, k = 400_000, 768, 100
+    pc = PackedCorpus(N, 1, d, DEV)
+    S.fill_packed_corpus(pc, seed=27)
+    mu = S.corpus_mean(d, 27, DEV)
+    r = MultiFieldRetriever(pc, LinearWeights(d, 1, query_cond=True).to(DEV), top_k=k)
+    q = S.make_queries(384, d, mu, 28, DEV)
+    s1, i1 = r.search(q, q.float(), impl="tcgen05")
+    s2, i2 = r.search(q, q.float(), impl="tcgen05_qs")
+    assert (s2[:, :-1] >= s2[:, 1:]).all()
+    assert all(len(set(row.tolist())) == k for row in i2.cpu())
+    torch.testing.assert_close(s1, s2, rtol=2e-5, atol=1e-4)
+    assert (i1 == i2).float().mean().item() > 0.98
+    qb = S.make_queries(1024, d, mu, 29, DEV)
+    sa, ia = r.search(qb, qb.float())
+    sb, ib = r.search(qb[:512], qb[:512].float())
+    sc, ic = r.search(qb[512:], qb[512:].float())
+    assert torch.equal(ia, torch.cat([ib, ic])) and torch.equal(sa, torch.cat([sb, sc]))
 
 
 def test_full_size_properties_10m_docs():
