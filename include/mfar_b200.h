@@ -178,6 +178,27 @@ MFAR_API int mfar_bm25_scores(const void* const* indptr_host, const void* const*
                               int64_t n_docs, float* out, int64_t ld, int zero_first, void* plan, size_t plan_bytes,
                               void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Producer of the precomputed-BM25 score files the COO input above consumes.  Replaces
+ * precompute_score_for_field (mfar/commands/precompute_bm25s_scores.py:12-30) over
+ * BM25sSparseIndex.get_scores_sparse (mfar/data/index.py:78-84): of a batch of full-corpus score rows
+ * `scores` fp32 [Q, ld] (mfar_bm25_scores output) keep the entries that are != 0 and whose doc is in the
+ * safe set, as pairs (qids[q], doc_id_base + row) int32 [nnz, 2] + one value per pair (np.float16(score):
+ * MFAR_F16, round-to-nearest; or MFAR_F32), ordered by (query row, doc) - the order the reference appends.
+ *   safe_bits: bit (doc_id_base + row) of a uint32 bitmap over GLOBAL doc ids, or NULL = every doc is safe;
+ *   qids: int32 [Q] query ids written into the pairs, or NULL = the row number;
+ *   seg_offsets: int64 [mfar_sparse_coo_offsets_len(Q, n_docs)] scratch.  mfar_sparse_coo_count fills it with
+ *     exclusive offsets per (query, 4096-doc segment); its LAST element is nnz: read it back (the one host
+ *     round trip), allocate out_keys [nnz,2] / out_vals [nnz], then call mfar_sparse_coo_write with the same
+ *     arguments.  No atomics: the output is deterministic.
+ * ------------------------------------------------------------------------------------------ */
+MFAR_API int64_t mfar_sparse_coo_offsets_len(int Q, int64_t n_docs);
+MFAR_API int mfar_sparse_coo_count(const float* scores, int64_t ld, int Q, int64_t n_docs, const uint32_t* safe_bits,
+                                   int64_t doc_id_base, int64_t* seg_offsets, void* stream);
+MFAR_API int mfar_sparse_coo_write(const float* scores, int64_t ld, int Q, int64_t n_docs, const uint32_t* safe_bits,
+                                   const int32_t* qids, int64_t doc_id_base, const int64_t* seg_offsets,
+                                   int32_t* out_keys, void* out_vals, int vals_dtype, void* stream);
+
 /* mfar_score_topk with the sparse fields given as BM25 postings + query tokens instead of score tensors:
  * workspace must hold mfar_score_topk_bm25_workspace_bytes(...). */
 MFAR_API size_t mfar_score_topk_bm25_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse, int64_t n_entries);

@@ -349,6 +349,46 @@ int mfar_bm25_scores(const void* const* indptr_host, const void* const* indices_
   return MFAR_OK;
 }
 
+static int check_sparse_coo(const float* scores, int64_t ld, int Q, int64_t n_docs, int64_t doc_id_base,
+                            const void* seg_offsets) {
+  if (!scores || !seg_offsets || Q <= 0 || n_docs <= 0 || ld < n_docs || doc_id_base < 0) return MFAR_ERR_ARG;
+  if (doc_id_base + n_docs > int64_t(0x7fffffff) || Q > 65535) return MFAR_ERR_SHAPE;   // int32 doc ids in the files
+  return MFAR_OK;
+}
+
+int64_t mfar_sparse_coo_offsets_len(int Q, int64_t n_docs) {
+  if (Q <= 0 || n_docs <= 0) return 0;
+  return int64_t(Q) * sparse_coo_segments(n_docs) + 1;
+}
+
+int mfar_sparse_coo_count(const float* scores, int64_t ld, int Q, int64_t n_docs, const uint32_t* safe_bits,
+                          int64_t doc_id_base, int64_t* seg_offsets, void* stream) {
+  t_last_launches = 0;
+  if (int rc = check_sparse_coo(scores, ld, Q, n_docs, doc_id_base, seg_offsets)) return rc;
+  if (int rc = check_arch()) return rc;
+  if (int rc = launch_sparse_coo_count(scores, ld, Q, n_docs, safe_bits, doc_id_base,
+                                       reinterpret_cast<long long*>(seg_offsets), static_cast<cudaStream_t>(stream)))
+    return rc;
+  t_last_launches = 2;
+  return MFAR_OK;
+}
+
+int mfar_sparse_coo_write(const float* scores, int64_t ld, int Q, int64_t n_docs, const uint32_t* safe_bits,
+                          const int32_t* qids, int64_t doc_id_base, const int64_t* seg_offsets, int32_t* out_keys,
+                          void* out_vals, int vals_dtype, void* stream) {
+  t_last_launches = 0;
+  if (int rc = check_sparse_coo(scores, ld, Q, n_docs, doc_id_base, seg_offsets)) return rc;
+  if (!out_keys || !out_vals || reinterpret_cast<uintptr_t>(out_keys) % 8 != 0) return MFAR_ERR_ARG;
+  if (vals_dtype != MFAR_F16 && vals_dtype != MFAR_F32) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  if (int rc = launch_sparse_coo_write(scores, ld, Q, n_docs, safe_bits, qids, doc_id_base,
+                                       reinterpret_cast<const long long*>(seg_offsets), out_keys, out_vals, vals_dtype,
+                                       static_cast<cudaStream_t>(stream)))
+    return rc;
+  t_last_launches = 1;
+  return MFAR_OK;
+}
+
 size_t mfar_score_topk_bm25_workspace_bytes(int Q, int k, int64_t n_docs, int n_sparse, int64_t n_entries) {
   const size_t b = mfar_score_topk_workspace_bytes(Q, k, n_docs, n_sparse);
   return b ? b + bm25_plan_bytes(n_entries) : 0;

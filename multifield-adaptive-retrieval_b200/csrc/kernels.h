@@ -23,6 +23,14 @@ int launch_bm25_build_scores(const int* post_token, const int* post_doc, const i
                              const int* df, const int* doc_len, long long n_docs_total, double l_avg, double k1,
                              double b, float* data, cudaStream_t st);
 
+// Dense score rows -> COO pairs in the reference's precomputed-BM25 file layout (sparse_coo.cu).
+long long sparse_coo_segments(long long n_docs);
+int launch_sparse_coo_count(const float* scores, long long ld, int Q, long long n_docs, const uint32_t* safe_bits,
+                            long long doc_id_base, long long* seg_offsets, cudaStream_t st);
+int launch_sparse_coo_write(const float* scores, long long ld, int Q, long long n_docs, const uint32_t* safe_bits,
+                            const int* qids, long long doc_id_base, const long long* seg_offsets, int* out_keys,
+                            void* out_vals, int vals_dtype, cudaStream_t st);
+
 int launch_pack_rows(const void* src, int src_dtype, int64_t n_rows, int64_t row_begin, void* packed,
                      int n_fields, int field, int dim, int normalize, cudaStream_t st);
 int launch_unpack_rows(const void* packed, int n_fields, int field, int dim, int64_t row_begin, int64_t n_rows,

@@ -47,6 +47,9 @@ PROTOTYPES = {
     "mfar_bm25_build_scores": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _f64, _f64, _f64, _vp, _vp]),
     "mfar_bm25_plan_bytes": (_sz, [_i64]),
     "mfar_bm25_scores": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i64, _i, _vp, _i, _i, _i64, _vp, _i64, _i, _vp, _sz, _vp]),
+    "mfar_sparse_coo_offsets_len": (_i64, [_i, _i64]),
+    "mfar_sparse_coo_count": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp, _vp]),
+    "mfar_sparse_coo_write": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
     "mfar_score_topk_bm25_workspace_bytes": (_sz, [_i, _i, _i64, _i, _i64]),
     "mfar_score_topk_bm25": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i64, _i64, _i,
                                   _vp, _vp, _vp, _vp, _sz, _i, _vp]),

@@ -78,6 +78,54 @@ def token_entries(vocab_dicts: Sequence[Optional[Dict[str, int]]],
     return np.concatenate(rows) if rows else np.zeros((0, 3), dtype=np.int32)
 
 
+def safe_docs_bitmap(safe_docs, n_docs_total: int) -> np.ndarray:
+    """uint32 bitmap over global doc ids (bit d set <=> d in ``safe_docs``) - the membership test of
+    ``get_scores_sparse`` (index.py:82-83) in the form ``mfar_sparse_coo_count/write`` take.  Ids outside
+    ``[0, n_docs_total)`` can never be hit by a score row and are dropped."""
+    bits = np.zeros((int(n_docs_total) + 31) // 32, dtype=np.uint32)
+    ids = np.fromiter((int(d) for d in safe_docs), dtype=np.int64)
+    ids = ids[(ids >= 0) & (ids < n_docs_total)]
+    np.bitwise_or.at(bits, ids >> 5, (np.uint32(1) << (ids & 31).astype(np.uint32)))
+    return bits
+
+
+def rows_to_coo(scores: torch.Tensor, n_docs: int, safe_bits: Optional[torch.Tensor] = None,
+                qids: Optional[torch.Tensor] = None, doc_id_base: int = 0,
+                vals_dtype: torch.dtype = torch.float16) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Dense score rows fp32 [Q, ld] (device) -> the pairs ``precompute_score_for_field`` writes
+    (precompute_bm25s_scores.py:19-27): keys int32 [nnz,2] = (qid, doc), vals [nnz] = np.float16(score), entries
+    != 0 whose doc is in the safe set, ordered (query row, doc).  Two device passes (count + scan, write) and ONE
+    host read of nnz in between; see csrc/sparse_coo.cu."""
+    nv.require_device(scores, "scores")
+    if scores.dtype != torch.float32 or scores.dim() != 2 or scores.stride(1) != 1:
+        raise ValueError("scores must be fp32 [Q, ld] with unit column stride")
+    if vals_dtype not in (torch.float16, torch.float32):
+        raise ValueError("vals_dtype must be float16 (the reference's file dtype) or float32")
+    Q, ld = scores.shape[0], scores.stride(0)
+    dev = scores.device
+    if safe_bits is not None:
+        nv.require_device(safe_bits, "safe_bits")
+        if safe_bits.dtype not in (torch.int32, torch.uint32) or safe_bits.numel() * 32 < doc_id_base + n_docs:
+            raise ValueError("safe_bits must be a 32-bit bitmap covering every global doc id of this shard")
+    if qids is not None:
+        qids = qids.to(dev, torch.int32).contiguous()
+        if qids.numel() != Q:
+            raise ValueError(f"need {Q} query ids, got {qids.numel()}")
+    lib = nv.lib()
+    offs = torch.empty(lib.mfar_sparse_coo_offsets_len(Q, n_docs), dtype=torch.int64, device=dev)
+    nv.check(lib.mfar_sparse_coo_count(nv.ptr(scores), ld, Q, n_docs, nv.ptr(safe_bits), doc_id_base, nv.ptr(offs),
+                                       nv.stream()), "sparse_coo_count")
+    nnz = int(offs[-1].item())
+    keys = torch.empty((nnz, 2), dtype=torch.int32, device=dev)
+    vals = torch.empty((nnz,), dtype=vals_dtype, device=dev)
+    if nnz:
+        nv.check(lib.mfar_sparse_coo_write(nv.ptr(scores), ld, Q, n_docs, nv.ptr(safe_bits), nv.ptr(qids), doc_id_base,
+                                           nv.ptr(offs), nv.ptr(keys), nv.ptr(vals),
+                                           nv.F16 if vals_dtype == torch.float16 else nv.F32, nv.stream()),
+                 "sparse_coo_write")
+    return keys, vals
+
+
 class DeviceBM25:
     """``bm25s.BM25`` with the score matrix in HBM.
 

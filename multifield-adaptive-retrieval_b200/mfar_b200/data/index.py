@@ -120,9 +120,11 @@ class BM25sSparseIndex(Index[str, str]):
         self.name = None
         self._score_cache: Dict[str, np.ndarray] = {}
         self._cache_size = 2 ** 15                                   # index.py:71
+        self._safe_bits = None                                       # device bitmap of safe_docs (lazy)
 
     def set_safe_docs(self, safe_docs):
         self.safe_docs = safe_docs
+        self._safe_bits = None
 
     def tokenize(self, queries, stopwords="en", stemmer=None, return_ids: bool = False):
         """index.py:55-69 with return_ids=False: token list for a str, list of token lists for a sequence."""
@@ -147,6 +149,25 @@ class BM25sSparseIndex(Index[str, str]):
         """index.py:78-84: nonzero scores of the docs in ``safe_docs``."""
         dense = self.get_scores(query)
         return {int(i): dense[i] for i in np.nonzero(dense)[0] if int(i) in self.safe_docs}
+
+    def get_scores_sparse_batch(self, queries: Sequence[str], query_ids: Optional[Sequence[int]] = None,
+                                vals_dtype=torch.float16) -> Tuple[np.ndarray, np.ndarray]:
+        """``get_scores_sparse`` (index.py:78-84) for a whole batch, in the array form the reference's
+        ``precompute_score_for_field`` turns the dicts into (precompute_bm25s_scores.py:19-27): keys int32 [nnz,2] =
+        (query id, doc id), vals float16 [nnz]; entries != 0 whose doc id is in ``safe_docs``, queries in the given
+        order, docs ascending.  The score rows never leave the device: one scatter pass writes them
+        (``mfar_bm25_scores``), two passes filter + compact them (``mfar_sparse_coo_count/write``) and only the nnz
+        pairs cross PCIe.  ``query_ids`` defaults to the row numbers."""
+        from .bm25 import rows_to_coo, safe_docs_bitmap
+        if self._safe_bits is None:
+            total = self.index.doc_base + self.index.num_docs
+            self._safe_bits = torch.from_numpy(safe_docs_bitmap(self.safe_docs, total).view(np.int32)).to(
+                self.index.device)
+        tokens = self.tokenize(list(queries), stopwords="en", stemmer=self.stemmer)
+        sv = self.index.get_scores_batch(tokens)                     # [Q, N] view of the fp32 [Q, 1, ld] rows
+        qids = None if query_ids is None else torch.tensor([int(x) for x in query_ids], dtype=torch.int32)
+        keys, vals = rows_to_coo(sv, self.index.num_docs, self._safe_bits, qids, self.index.doc_base, vals_dtype)
+        return keys.cpu().numpy(), vals.cpu().numpy()
 
     def retrieve(self, query: str, top_k: int):
         return self.retrieve_batch([query], top_k)[0]                # index.py:86-93

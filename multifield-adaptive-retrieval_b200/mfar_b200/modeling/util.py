@@ -92,9 +92,9 @@ def read_and_create_indices(corpus_path: str, dataset_name: str, field_info: Dic
     keys: List[str] = [x[0] for x in corpus]
     key_to_row = {k: i for i, k in enumerate(keys)}
     vectors_dict, indices_dict = {}, {}
-    dim = encoder.get_sentence_embedding_dimension()
     for field_key, field in field_info.items():
         if field.field_type == FieldType.DENSE:
+            dim = encoder.get_sentence_embedding_dimension()           # sparse-only callers pass encoder=None
             v_file = f"{temp_dir}/{field.name}.npy"                    # name, not key (modeling/util.py:85)
             Path(v_file).parents[0].mkdir(parents=True, exist_ok=True)
             with open(v_file, "w"):

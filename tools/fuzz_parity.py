@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Randomised parity sweep of the scoring kernels against the CPU oracle (needs a B200; not part of pytest).
+
+    python tools/fuzz_parity.py --seconds 120 --seed 0 --out gpurun_out/fuzz.json
+
+Draws shapes across the envelope every kernel claims (doc counts around the 128-doc tile and 64-doc half-tile
+boundaries, dims 32..1024 incl. ones that are not a multiple of 64, 0..6 dense and 0..3 sparse fields, batches around
+the 16/32/64/128/256 query-tile boundaries, k 1..128, masks, doc-id bases, f16/f32 sparse inputs, all four impl
+requests) and applies the same assertion as tests/parity.py.  Every failure is recorded with its parameters; the
+exit code is the number of failures (0 = clean).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (os.path.join(ROOT, "multifield-adaptive-retrieval_b200"), os.path.join(ROOT, "oracle"),
+           os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import mfar_oracle as O  # noqa: E402  (checker)
+from parity import assert_topk_parity  # noqa: E402
+
+
+def draw_case(rng: np.random.RandomState) -> dict:
+    n_choices = [1, 2, 63, 64, 65, 127, 128, 129, 191, 192, 193, 255, 256, 257, 1000, 4095, 4097]
+    N = int(rng.choice(n_choices)) if rng.rand() < 0.6 else int(rng.randint(1, 20000))
+    d = int(rng.choice([32, 64, 100, 128, 192, 256, 320, 768, 1024]))
+    Fd = int(rng.choice([0, 1, 1, 2, 3, 5, 6]))
+    Fs = int(rng.choice([0, 0, 1, 2, 3]))
+    if Fd + Fs == 0:
+        Fd = 1
+    q_choices = [1, 2, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 300]
+    Q = int(rng.choice(q_choices))
+    if N * max(Fd, 1) * d > 2.5e7 or Q * N * max(Fs, 1) > 1.2e7:       # keep the fp32 oracle in the seconds range
+        N = max(1, min(N, int(2.5e7 / (max(Fd, 1) * d)), int(1.2e7 / (Q * max(Fs, 1)))))
+    k = int(min(N, rng.choice([1, 2, 10, 50, 100, 100, 127, 128])))
+    impl = str(rng.choice(["auto", "simt", "tcgen05", "tcgen05_qs"]))
+    if Fd == 0 or d % 64 != 0:                                          # tensor-core paths need dim % 64 == 0 ...
+        impl = str(rng.choice(["auto", "simt"]))                        # (PackedCorpus pads dim, so "auto" still may)
+    if impl == "tcgen05_qs" and d > 768:                                # queries must fit 384 TMEM columns
+        impl = "tcgen05"
+    return dict(N=N, d=d, Fd=Fd, Fs=Fs, Q=Q, k=k, impl=impl, query_cond=bool(rng.rand() < 0.6),
+                base=int(rng.choice([0, 0, 12345, 3_000_000_000])), sparse_f32=bool(rng.rand() < 0.4),
+                n_masked=int(rng.randint(0, 2)) if Fd + Fs > 1 else 0, normalize=bool(rng.rand() < 0.15),
+                seed=int(rng.randint(0, 2 ** 31 - 1)))
+
+
+def run_case(c: dict) -> None:
+    from mfar_b200.modeling.retrieval import MultiFieldRetriever, PackedCorpus
+    from mfar_b200.modeling.weighting import LinearWeights
+    dev = "cuda"
+    g = torch.Generator().manual_seed(c["seed"])
+    N, d, Fd, Fs, Q, k = c["N"], c["d"], c["Fd"], c["Fs"], c["Q"], c["k"]
+    mu = torch.randn(d, generator=g)
+    raw = [torch.randn(N, d, generator=g) + 0.5 * mu for _ in range(Fd)]
+    qraw = torch.randn(Q, d, generator=g) + 0.5 * mu
+    if c["normalize"]:                              # oracle side of Normalize(): fp32 normalise, then bf16 rounding
+        fields = [O.round_bf16(torch.nn.functional.normalize(f, dim=1)) for f in raw]
+        q = O.round_bf16(torch.nn.functional.normalize(qraw, dim=1))
+    else:
+        fields = [O.round_bf16(f) for f in raw]
+        q = O.round_bf16(qraw)
+        raw, qraw = fields, q
+    sp = None
+    if Fs:
+        u = torch.rand(Q, Fs, N, generator=g)
+        sp = torch.where(u < 0.9, torch.zeros(()), 8.0 * torch.rand(Q, Fs, N, generator=g)).half()
+    F = Fd + Fs
+    qc = c["query_cond"]
+    W = 0.05 * torch.randn(d, F, generator=g) if qc else torch.randn(F, 1, generator=g)
+    layer = LinearWeights(d, F, query_cond=True) if qc else LinearWeights(F, 1)
+    with torch.no_grad():
+        layer.weight.copy_(W)
+    pc = PackedCorpus.from_fields(raw, dev, c["normalize"]) if Fd else None
+    r = MultiFieldRetriever(pc, layer.to(dev), n_sparse=Fs, top_k=k, doc_id_base=c["base"], impl=c["impl"], n_docs=N,
+                            device=dev)
+    mask = torch.ones(F, 1)
+    if c["n_masked"]:
+        idx = [int(c["seed"] % F)]
+        mask[idx] = 0
+        r.mask_field(idx)
+    sp_in = None if sp is None else (sp.float() if c["sparse_f32"] else sp).to(dev)
+    q_emb = qraw.to(dev) if not c["normalize"] else q.to(dev)
+    scores, ids = r.search(qraw.to(dev) if Fd else None, q_emb, sp_in)
+    torch.cuda.synchronize()
+    w = O.mixture_weights(q_emb.float().cpu() if qc else None, W, qc)
+    ref = O.exhaustive_scores(q, fields, None if sp is None else sp.float(), w, mask)
+    rtol = 2e-5 if not c["normalize"] else 2e-3     # device-side normalisation rounds to bf16 from a device rsqrt
+    assert_topk_parity(scores.cpu().numpy(), ids.cpu().numpy(), ref.numpy(), k, id_offset=c["base"], rtol=rtol,
+                       tie_rel=1e-5 if not c["normalize"] else 2e-3)
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=120.0)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "fuzz.json"))
+    args = ap.parse_args()
+    rng = np.random.RandomState(args.seed)
+    t0 = time.time()
+    n, failures, per_impl = 0, [], {}
+    while time.time() - t0 < args.seconds:
+        c = draw_case(rng)
+        n += 1
+        per_impl[c["impl"]] = per_impl.get(c["impl"], 0) + 1
+        try:
+            run_case(c)
+        except Exception as e:  # noqa: BLE001  (recorded, sweep goes on)
+            failures.append(dict(case=c, error=f"{type(e).__name__}: {e}"[:600], trace=traceback.format_exc()[-1500:]))
+            print("FAIL", json.dumps(c), str(e)[:200], flush=True)
+            if "CUDA error" in str(e) or "illegal" in str(e).lower():
+                break                                                   # sticky context error: nothing more to learn
+    res = dict(cases=n, failures=len(failures), seconds=round(time.time() - t0, 1), per_impl=per_impl, seed=args.seed,
+               failed=failures)
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps({k: v for k, v in res.items() if k != "failed"}))
+    return len(failures)
+
+
+if __name__ == "__main__":
+    sys.exit(min(main(), 100))
