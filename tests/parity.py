@@ -42,3 +42,24 @@ def assert_topk_parity(got_scores, got_ids, all_scores, k, tie_rel=TIE_REL, rtol
         # order: position p holds a doc whose oracle score near-ties the oracle's p-th score
         assert np.all(np.abs(s[ids] - s[order]) <= tol + rtol * scale), f"q{q}: rank order differs beyond near-ties"
     return True
+
+
+def assert_same_topk_up_to_ties(s_a, i_a, s_b, i_b, rel=TIE_REL):
+    """Two CUDA runs of the same search whose scores may differ in the last bits (fp32 atomics of the BM25 scatter
+    add in a run-dependent order): rank-wise scores agree within ``rel`` of the row's scale, and an id that sits at a
+    different rank (or dropped out at the k-th boundary) must near-tie the score found at that rank / the k-th."""
+    s_a, s_b = np.asarray(s_a, dtype=np.float64), np.asarray(s_b, dtype=np.float64)
+    i_a, i_b = np.asarray(i_a), np.asarray(i_b)
+    assert s_a.shape == s_b.shape == i_a.shape == i_b.shape
+    if s_a.ndim == 1:
+        s_a, s_b, i_a, i_b = s_a[None], s_b[None], i_a[None], i_b[None]
+    for q in range(s_a.shape[0]):
+        tol = rel * max(1e-30, np.abs(s_a[q]).max())
+        np.testing.assert_allclose(s_a[q], s_b[q], rtol=0, atol=tol, err_msg=f"q{q}: rank-wise scores")
+        pos_b = {int(d): p for p, d in enumerate(i_b[q])}
+        for p in np.nonzero(i_a[q] != i_b[q])[0]:
+            d = int(i_a[q, p])
+            if d in pos_b:
+                assert abs(s_b[q, pos_b[d]] - s_a[q, p]) <= tol, f"q{q}: doc {d} moved between non-tied ranks"
+            else:
+                assert s_a[q, p] - s_a[q, -1] <= tol, f"q{q}: doc {d} missing without tying the k-th score"

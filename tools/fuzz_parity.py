@@ -100,8 +100,116 @@ def run_case(c: dict) -> None:
                        tie_rel=1e-5 if not c["normalize"] else 2e-3)
 
 
+def draw_api_case(rng: np.random.RandomState) -> dict:
+    c = draw_case(rng)
+    c["impl"] = "auto"
+    c["normalize"] = False
+    c["Fd"] = max(1, c["Fd"])
+    c["N"] = max(c["N"], 2)
+    c["k"] = int(min(c["k"], c["N"]))
+    c["base"] = int(rng.choice([0, 777]))
+    return c
+
+
+def run_api_case(c: dict) -> None:
+    """One shape through every entry path that must agree: device search, the host-buffer C call, the COO sparse
+    input, doc-range shards + merge, the CUDA-graph replay, the one-pass mask sweep, per-field top-k, union_rescore."""
+    from mfar_b200.dist import merge_keys
+    from mfar_b200.modeling.retrieval import GraphedSearch, MultiFieldRetriever, PackedCorpus
+    from mfar_b200.modeling.weighting import LinearWeights
+    dev = "cuda"
+    g = torch.Generator().manual_seed(c["seed"])
+    N, d, Fd, Fs, Q, k, base = c["N"], c["d"], c["Fd"], c["Fs"], c["Q"], c["k"], c["base"]
+    mu = torch.randn(d, generator=g)
+    fields = [O.round_bf16(torch.randn(N, d, generator=g) + 0.5 * mu) for _ in range(Fd)]
+    q = O.round_bf16(torch.randn(Q, d, generator=g) + 0.5 * mu)
+    sp = None
+    if Fs:
+        u = torch.rand(Q, Fs, N, generator=g)
+        sp = torch.where(u < 0.9, torch.zeros(()), 8.0 * torch.rand(Q, Fs, N, generator=g)).half()
+    F = Fd + Fs
+    qc = c["query_cond"]
+    W = 0.05 * torch.randn(d, F, generator=g) if qc else torch.randn(F, 1, generator=g)
+    layer = LinearWeights(d, F, query_cond=True) if qc else LinearWeights(F, 1)
+    with torch.no_grad():
+        layer.weight.copy_(W)
+    layer = layer.to(dev)
+
+    def make(lo, hi):
+        return MultiFieldRetriever(PackedCorpus.from_fields([f[lo:hi] for f in fields], dev), layer, n_sparse=Fs,
+                                   top_k=k, doc_id_base=base + lo)
+    r = make(0, N)
+    mask = torch.ones(F, 1)
+    if c["n_masked"]:
+        idx = [int(c["seed"] % F)]
+        mask[idx] = 0
+        r.mask_field(idx)
+    qd, spd = q.to(dev), (None if sp is None else sp.to(dev))
+    w = O.mixture_weights(q if qc else None, W, qc)
+    ref = O.exhaustive_scores(q, fields, None if sp is None else sp.float(), w, mask).numpy()
+    s0, i0, k0 = r.search(qd, qd, spd, return_keys=True)
+    assert_topk_parity(s0.cpu().numpy(), i0.cpu().numpy(), ref, k, id_offset=base)
+    # host-buffer C call == device call, bit for bit
+    qh = r.corpus.prepare_queries(q).cpu().pin_memory()
+    s_h, i_h = r.search_host(qh, q.float().pin_memory() if qc else None, None if sp is None else sp.pin_memory())
+    assert torch.equal(s_h, s0.cpu()) and torch.equal(i_h, i0.cpu()), "search_host != search"
+    # COO sparse input (global doc ids) vs the oracle
+    if Fs:
+        ks, vs, offs = [], [], [0]
+        for j in range(Fs):
+            nz = torch.nonzero(sp[:, j, :])
+            ks.append(torch.stack([nz[:, 0], nz[:, 1] + base], dim=1).int())
+            vs.append(sp[nz[:, 0], j, nz[:, 1]])
+            offs.append(offs[-1] + len(nz))
+        coo = (torch.cat(ks).to(dev), torch.cat(vs).to(dev), offs)
+        s_c, i_c = r.search(qd, qd, sparse_coo=coo)
+        assert_topk_parity(s_c.cpu().numpy(), i_c.cpu().numpy(), ref, k, id_offset=base)
+    # doc-range shards (arbitrary, not tile-aligned cut) merged == unsharded, bit for bit
+    cut = 1 + int(c["seed"] % (N - 1))
+    keys = []
+    for lo, hi in ((0, cut), (cut, N)):
+        sh = make(lo, hi)
+        sh.mask = r.mask
+        kk = sh.search(qd, qd, None if spd is None else spd[:, :, lo:hi].contiguous(), top_k=min(k, hi - lo),
+                       return_keys=True)[2]
+        keys.append(torch.nn.functional.pad(kk, (0, k - kk.shape[1])))
+    s_m, i_m = merge_keys(torch.stack(keys), k)
+    assert torch.equal(i_m, i0) and torch.equal(s_m, s0), "shard merge != unsharded"
+    # CUDA-graph replay == eager
+    gs = GraphedSearch(r, Q, sparse="dense" if Fs else "none", sparse_ld=None if sp is None else N)
+    s_g, i_g = gs(qd, qd.float(), sparse=spd)
+    assert torch.equal(s_g, s0) and torch.equal(i_g, i0), "graph replay != eager"
+    # one-pass mask sweep == mask_field loop (vs the oracle)
+    if F > 1:
+        sets = [[], [0], [F - 1], list(range(0, F, 2))]
+        S, I = r.search_mask_sweep(qd, sets, qd, spd, max_rows=max(Q, 300))
+        for m, idx in enumerate(sets):
+            mm = torch.ones(F, 1)
+            mm[idx] = 0
+            ref_m = O.exhaustive_scores(q, fields, None if sp is None else sp.float(), w, mm).numpy()
+            assert_topk_parity(S[m].cpu().numpy(), I[m].cpu().numpy(), ref_m, k, id_offset=base)
+    # per-field top-k incl. the zero-init quirk, and the faithful union_rescore pipeline, vs the oracle
+    ps, pr = r.per_field_topk(qd, spd, k)
+    for f in range(Fd):
+        rs, rr = O.dense_retrieve_batch(q, fields[f], k)
+        np.testing.assert_allclose(ps[f].cpu().numpy(), rs.numpy(), rtol=2e-5, atol=2e-5 * float(rs.abs().max() + 1e-30))
+    if Q <= 33 and Fs == 0:                 # (sparse per-field top-k reaches into exact-zero ties: union order unpinned)
+        try:
+            want_v, want_r = O.union_rescore(q, fields, None if sp is None else sp.float(), q if qc else None, W, qc,
+                                             mask, k)
+        except RuntimeError:
+            want_v = None                       # union smaller than k: the reference's torch.topk raises
+        if want_v is not None:
+            got_v, got_r = r.union_rescore(qd, qd, spd)
+            for i in range(Q):
+                wv = want_v[i].numpy()
+                np.testing.assert_allclose(got_v[i].cpu().numpy(), wv, rtol=2e-5, atol=2e-5 * float(np.abs(wv).max() + 1e-30))
+    torch.cuda.synchronize()
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="kernels", choices=["kernels", "api"])
     ap.add_argument("--seconds", type=float, default=120.0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "fuzz.json"))
@@ -110,17 +218,17 @@ def main() -> int:
     t0 = time.time()
     n, failures, per_impl = 0, [], {}
     while time.time() - t0 < args.seconds:
-        c = draw_case(rng)
+        c = draw_case(rng) if args.mode == "kernels" else draw_api_case(rng)
         n += 1
         per_impl[c["impl"]] = per_impl.get(c["impl"], 0) + 1
         try:
-            run_case(c)
+            run_case(c) if args.mode == "kernels" else run_api_case(c)
         except Exception as e:  # noqa: BLE001  (recorded, sweep goes on)
             failures.append(dict(case=c, error=f"{type(e).__name__}: {e}"[:600], trace=traceback.format_exc()[-1500:]))
             print("FAIL", json.dumps(c), str(e)[:200], flush=True)
             if "CUDA error" in str(e) or "illegal" in str(e).lower():
                 break                                                   # sticky context error: nothing more to learn
-    res = dict(cases=n, failures=len(failures), seconds=round(time.time() - t0, 1), per_impl=per_impl, seed=args.seed,
+    res = dict(mode=args.mode, cases=n, failures=len(failures), seconds=round(time.time() - t0, 1), per_impl=per_impl, seed=args.seed,
                failed=failures)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
