@@ -261,3 +261,29 @@ def test_header_is_valid_c_and_links_against_the_library(tmp_path):
                     "-o", str(exe), "-L", libdir, "-l:libmfar_b200.so", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split(" ", 1)
     assert int(out[0]) == len(names) == len(nv.PROTOTYPES) and "sm_100" in out[1]
+
+
+def test_sweep_case_generators_stay_inside_the_kernels_envelope():
+    """tools/fuzz_parity.py draws (the GPU sweep itself needs a B200): k <= N, at least one field, the tensor-core
+    requests only where the C ABI accepts them (dim % 64 == 0, a dense field; query-stationary: dim <= 768)."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_parity as F
+    rng = np.random.RandomState(0)
+    for _ in range(500):
+        c = F.draw_case(rng)
+        assert 1 <= c["k"] <= c["N"] and c["k"] <= 128 and c["Fd"] + c["Fs"] >= 1
+        if c["impl"] in ("tcgen05", "tcgen05_qs"):
+            assert c["Fd"] >= 1 and c["d"] % 64 == 0
+        if c["impl"] == "tcgen05_qs":
+            assert c["d"] <= 768
+        assert c["base"] + c["N"] <= 2 ** 32
+        a = F.draw_api_case(rng)
+        assert a["Fd"] >= 1 and 2 <= a["N"] and a["k"] <= a["N"] and a["impl"] == "auto"
+        b = F.draw_bm25_case(rng)
+        assert b["N"] >= 1 and b["V"] >= 1 and b["Fs"] >= 1
+        t = F.draw_train_case(rng)
+        assert t["E"] % 4 == 0 and t["E"] <= 1024
+    assert set(F.MODES) == {"kernels", "api", "bm25", "train"}
