@@ -78,3 +78,47 @@ def test_c_abi_argument_checks_without_a_gpu():
     assert lib.mfar_sparse_coo_count(256, 10, 1, 10, 0, 2**31 - 5, 256, 0) == 2          # doc ids beyond int32
     assert lib.mfar_sparse_coo_write(256, 10, 1, 10, 0, 0, 0, 256, 0, 0, nv.F16, 0) == 1  # null outputs
     assert lib.mfar_sparse_coo_write(256, 10, 1, 10, 0, 0, 0, 256, 256, 256, nv.BF16, 0) == 1
+
+
+class _FakeSparseIndex:
+    """Host stand-in for BM25sSparseIndex (the device class is covered by test_gpu_precompute.py): serves given score
+    rows through the same two methods the command calls."""
+
+    def __init__(self, rows_by_text):
+        self.rows, self.safe, self.batches = rows_by_text, None, []
+
+    def set_safe_docs(self, safe_docs):
+        self.safe = set(safe_docs)
+
+    def get_scores_sparse_batch(self, queries, query_ids=None):
+        self.batches.append(len(queries))
+        return PO.precompute_score_for_field({qid: self.rows[q] for qid, q in zip(query_ids, queries)}, self.safe)
+
+    def retrieve_batch(self, queries, top_k):
+        return [[(str(d), float(self.rows[q][d])) for d in np.argsort(-self.rows[q], kind="stable")[:top_k]] for q in queries]
+
+
+def test_command_host_logic_batches_orders_and_files(tmp_path):
+    from mfar_b200.commands import precompute_bm25s_scores as C
+    z, rows = _load([p for p in GOLDEN if p.endswith("pre_small.npz")][0])
+    qids = [int(q) for q in z["qids"]]
+    texts = {qid: f"text {i}" for i, qid in enumerate(qids)}
+    index = _FakeSparseIndex({texts[qid]: rows[qid] for qid in qids})
+    keys, vals = C.precompute_score_for_field(index, z["safe"].tolist(), texts, str(tmp_path), "f_sparse", batch_size=2)
+    assert index.batches == [2, 2, 1]                                   # 5 queries in batches of 2, order kept
+    np.testing.assert_array_equal(keys, z["ref_keys"])                  # == what the reference's function wrote
+    np.testing.assert_array_equal(vals.view(np.uint16), z["ref_vals"].view(np.uint16))
+    np.testing.assert_array_equal(np.load(tmp_path / "f_sparse_keys_bm25.npy"), z["ref_keys"])
+    assert np.load(tmp_path / "f_sparse_vals_bm25.npy").dtype == np.float16
+    # train.queries / train.qrels readers and the candidate set (top-k negatives united with the positives)
+    (tmp_path / "train.queries").write_text("".join(f"{qid}\t{texts[qid]}\n" for qid in qids))
+    (tmp_path / "train.qrels").write_text(f"{qids[0]}\t0\t7\t1\n{qids[1]}\t0\t299\t1\n")
+    queries, pos = C.read_queries_and_positives(str(tmp_path))
+    assert queries == texts and pos == {7, 299}
+    cand = C.candidate_docs(index, list(queries.values()), pos, top_k=3, batch_size=2)
+    want = {7, 299}
+    for q in queries.values():
+        want |= set(np.argsort(-index.rows[q], kind="stable")[:3].tolist())
+    assert cand == want
+    with pytest.raises(ValueError):
+        C.main(str(tmp_path), "mag", str(tmp_path), str(tmp_path), fields_str="all_dense")
