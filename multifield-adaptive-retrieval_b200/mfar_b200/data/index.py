@@ -126,6 +126,12 @@ class BM25sSparseIndex(Index[str, str]):
         self.safe_docs = safe_docs
         self._safe_bits = None
 
+    @staticmethod
+    def tokenize_single(query: str, stopwords="en", stemmer=None, return_ids: bool = False) -> List[str]:
+        """index.py:55-64 with return_ids=False: the token list of one query string."""
+        from .bm25 import tokenize
+        return tokenize(query, stopwords, stemmer)[0]
+
     def tokenize(self, queries, stopwords="en", stemmer=None, return_ids: bool = False):
         """index.py:55-69 with return_ids=False: token list for a str, list of token lists for a sequence."""
         from .bm25 import tokenize

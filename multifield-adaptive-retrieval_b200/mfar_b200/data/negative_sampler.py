@@ -11,25 +11,10 @@ from __future__ import annotations
 
 import random
 from abc import ABC
-from dataclasses import dataclass
-from typing import AbstractSet, Any, List, Mapping, Optional, Sequence, Tuple
+from typing import AbstractSet, List, Mapping, Sequence, Tuple
 
 from .index import Index
-
-
-@dataclass
-class Query:                     # mfar/data/typedef.py:13-17 (the fields the sampler touches)
-    _id: str
-    text: str
-    metadata: Any = None
-
-
-@dataclass
-class Document:                  # mfar/data/typedef.py:31-36
-    _id: str
-    text: str
-    title: Optional[str] = None
-    metadata: Any = None
+from .typedef import Document, Query
 
 
 class NegativeSampler(ABC):

@@ -1,13 +1,68 @@
-"""Field / FieldType - the two schema types the scoring path needs.
+"""Schema and text-container types of the scoring path (mfar/data/typedef.py).
 
-Mirrors mfar/data/typedef.py:69-122 (the reference's Query/Document/Corpus text containers
-are outside the hot path and not rebuilt).
+``Field`` / ``FieldType`` (typedef.py:69-122) order the scorer columns; ``Query`` / ``Document`` / ``Corpus``
+(typedef.py:13-67, 125-172) are the plain containers the callers either side of the path pass around
+(``IndexNegativeSampler``, ``BM25sSparseIndex.create``) - kept without the reference's JSON mixin, gzip readers and
+STaRK text formatting, which are data preparation.
 """
 from __future__ import annotations
 
 import json
+from dataclasses import dataclass
 from enum import Enum
-from typing import Optional
+from typing import Any, Dict, Iterator, List, Optional
+
+
+@dataclass
+class Query:                     # typedef.py:13-17
+    _id: str
+    text: str
+    metadata: Any = None
+
+
+@dataclass
+class Document:                  # typedef.py:31-36
+    _id: str
+    text: str
+    title: Optional[str] = None
+    metadata: Any = None
+
+
+@dataclass
+class Corpus:                    # typedef.py:125-172
+    docs: List[Document]
+    dataset_name: Optional[str] = None
+
+    def __post_init__(self):
+        self.key_to_id = {doc._id: i for i, doc in enumerate(self.docs)}
+
+    def keys(self) -> Iterator[str]:
+        return (doc._id for doc in self.docs)
+
+    def __len__(self) -> int:
+        return len(self.docs)
+
+    def get_text_by_id(self, doc_id: int) -> str:
+        return self.docs[doc_id].text
+
+    def get_text_by_key(self, key: str) -> str:
+        return self.docs[self.key_to_id[key]].text
+
+    def get_doc_by_id(self, doc_id: int) -> Document:
+        return self.docs[doc_id]
+
+    def get_doc_by_key(self, key: str) -> Document:
+        try:
+            return self.docs[self.key_to_id[key]]
+        except KeyError:
+            raise KeyError(f"Key {key} not found in corpus.")
+
+    def pairs(self):
+        return ((doc._id, doc.text) for doc in self.docs)
+
+    @classmethod
+    def from_docs_dict(cls, docs_dict: Dict[Any, str], dataset_name: Optional[str] = None) -> "Corpus":
+        return cls([Document(key, text) for key, text in docs_dict.items()], dataset_name)
 
 
 class FieldType(Enum):

@@ -40,3 +40,16 @@ def test_sample_batch_is_one_batched_retrieval_with_the_same_result():
         assert [[[d._id, d.text] for d in docs] for docs in got] == case["picked"]
         assert batched == [len(queries)]                                 # ONE retrieve_batch for the whole batch
         assert all(isinstance(d, Document) for docs in got for d in docs)
+
+
+def test_corpus_container_matches_reference_accessors():
+    from mfar_b200.data.typedef import Corpus
+    c = Corpus.from_docs_dict({"a": "alpha text", "b": "beta"}, dataset_name="mag")
+    assert list(c.keys()) == ["a", "b"] and len(c) == 2 and c.dataset_name == "mag"
+    assert c.get_text_by_id(1) == "beta" and c.get_text_by_key("a") == "alpha text"
+    assert c.get_doc_by_key("b")._id == "b" and list(c.pairs()) == [("a", "alpha text"), ("b", "beta")]
+    try:
+        c.get_doc_by_key("zzz")
+        raise AssertionError("expected KeyError")
+    except KeyError as e:
+        assert "not found in corpus" in str(e)
