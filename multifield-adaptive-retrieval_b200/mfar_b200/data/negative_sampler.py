@@ -10,62 +10,61 @@ per-query order, so it returns what the reference's loop returns for the same se
 from __future__ import annotations
 
 import random
-from abc import ABC
+from abc import ABC, abstractmethod
 from typing import AbstractSet, List, Mapping, Sequence, Tuple
 
 from .index import Index
 from .typedef import Document, Query
 
 
+Positives = Mapping[str, AbstractSet[str]]        # query id -> keys of its relevant docs
+
+
 class NegativeSampler(ABC):
-    @property
-    def n_sample(self) -> int:
-        raise NotImplementedError
+    """Interface of negative_sampler.py:10-20: ``n_sample`` docs per query, drawn for one query or a batch."""
 
-    def sample(self, query: Query, pos_for_each_qid: Mapping[str, AbstractSet[str]]) -> List[Document]:
-        raise NotImplementedError
+    n_sample: int
 
-    def sample_batch(self, queries: List[Query], pos_for_each_qid: Mapping[str, AbstractSet[str]]) -> List[List[Document]]:
-        raise NotImplementedError
+    @abstractmethod
+    def sample(self, query: Query, pos_for_each_qid: Positives) -> List[Document]: ...
+
+    def sample_batch(self, queries: List[Query], pos_for_each_qid: Positives) -> List[List[Document]]:
+        return [self.sample(q, pos_for_each_qid) for q in queries]
 
 
 class IndexNegativeSampler(NegativeSampler):
+    """negative_sampler.py:22-63.  ``documents`` maps doc key -> text (missing keys give an empty text)."""
+
     def __init__(self, index: Index, documents: Mapping[str, str], n_retrieve: int = 50, n_bottom: int = 5,
                  n_sample: int = 1):
-        self.index = index
-        self.documents = documents
-        self.n_retrieve = n_retrieve
-        self.n_bottom = n_bottom
-        self._n_sample = n_sample
+        self.index, self.documents = index, documents
+        self.n_retrieve, self.n_bottom, self._n_sample = n_retrieve, n_bottom, n_sample
 
     @property
     def n_sample(self) -> int:
         return self._n_sample
 
-    @staticmethod
-    def _negatives(hits: Sequence[Tuple[str, float]], positives: AbstractSet[str]) -> List[Tuple[str, float]]:
-        return [(doc_id, score) for doc_id, score in hits if doc_id not in positives]   # negative_sampler.py:41-45
+    def _retrieve_negatives(self, text: str, top_k: int, positives: AbstractSet[str],
+                            hits: Sequence[Tuple[str, float]] = None) -> List[Tuple[str, float]]:
+        """Retrieved (key, score) pairs minus the query's positives (negative_sampler.py:41-45)."""
+        if hits is None:
+            hits = self.index.retrieve(text, top_k=top_k)
+        return [(key, score) for key, score in hits if key not in positives]
 
-    def _draw(self, cands: List[Tuple[str, float]]) -> List[Document]:
-        cands.sort(key=lambda x: x[1], reverse=True)                                    # negative_sampler.py:53 (stable)
-        neg_cand_ids = [doc_id for doc_id, _ in cands[-self.n_bottom:]]
-        picked = [neg_cand_ids[i] for i in random.sample(range(len(neg_cand_ids)), self.n_sample)]
-        return [Document(i, self.documents.get(i, "")) for i in picked]
+    def _pick(self, query: Query, positives: AbstractSet[str], first_hits=None) -> List[Document]:
+        cands = self._retrieve_negatives(query.text, self.n_retrieve, positives, first_hits)
+        if not cands:                    # everything retrieved was relevant: look deeper once (negative_sampler.py:46-52)
+            cands = self._retrieve_negatives(query.text, len(positives) + self.n_bottom, positives)
+        cands.sort(key=lambda pair: pair[1], reverse=True)               # stable, like the reference's list.sort
+        bottom = [key for key, _ in cands[-self.n_bottom:]]              # the n_bottom lowest-scoring survivors
+        chosen = random.sample(range(len(bottom)), self.n_sample)        # same draw as negative_sampler.py:55
+        return [Document(bottom[i], self.documents.get(bottom[i], "")) for i in chosen]
 
-    def sample(self, query: Query, pos_for_each_qid: Mapping[str, AbstractSet[str]]) -> List[Document]:
-        pos = pos_for_each_qid[query._id]
-        cands = self._negatives(self.index.retrieve(query.text, top_k=self.n_retrieve), pos)
-        if len(cands) == 0:                                                             # negative_sampler.py:46-52
-            cands = self._negatives(self.index.retrieve(query.text, top_k=len(pos) + self.n_bottom), pos)
-        return self._draw(cands)
+    def sample(self, query: Query, pos_for_each_qid: Positives) -> List[Document]:
+        return self._pick(query, pos_for_each_qid[query._id])
 
-    def sample_batch(self, queries: List[Query], pos_for_each_qid: Mapping[str, AbstractSet[str]]) -> List[List[Document]]:
+    def sample_batch(self, queries: List[Query], pos_for_each_qid: Positives) -> List[List[Document]]:
+        """ONE ``retrieve_batch`` (one fused GPU pass) for the whole batch; the per-query filtering, the rare deeper
+        retry and the ``random`` draws then run in query order, so the result equals the reference's loop."""
         all_hits = self.index.retrieve_batch([q.text for q in queries], top_k=self.n_retrieve)
-        out = []
-        for q, hits in zip(queries, all_hits):
-            pos = pos_for_each_qid[q._id]
-            cands = self._negatives(hits, pos)
-            if len(cands) == 0:                         # every retrieved doc was a positive: the deeper retry, per query
-                cands = self._negatives(self.index.retrieve(q.text, top_k=len(pos) + self.n_bottom), pos)
-            out.append(self._draw(cands))
-        return out
+        return [self._pick(q, pos_for_each_qid[q._id], hits) for q, hits in zip(queries, all_hits)]
