@@ -29,6 +29,8 @@ for _p in (os.path.join(ROOT, "multifield-adaptive-retrieval_b200"), os.path.joi
 import torch  # noqa: E402
 
 METRIC = "queries/sec for multi-field top-100"
+NOMINAL_HBM_GBS = 8000.0        # north_star: "roughly 8 TB/s" (fractions against both, labelled)
+NOMINAL_BF16_TFLOPS = 2250.0    # dense bf16, B200 data sheet
 DIM = 768
 TOPK = 100
 GEN_CHUNK = 65536
@@ -114,6 +116,17 @@ def build_shard(n_total, n_fields, lo, hi, seed, device):
     return pc, mu
 
 
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def algorithmic_work(n_docs, n_dense, n_sparse, Q, sparse_bytes=2):
     """bytes = N*Fd*d*2 (+ Q*N*Fs*b_s) + small; flops = 2*Q*N*Fd*d."""
     bytes_ = n_docs * n_dense * DIM * 2 + Q * n_docs * n_sparse * sparse_bytes + Q * DIM * 2 + Q * TOPK * 12
@@ -183,6 +196,7 @@ def cpu_reference_leg(n_total, n_dense, n_sparse, Q, seed, budget_s, steps, warm
         "sample": (f"oracle union_rescore (faithful trec_eval_step port), fp32 torch CPU, {n_sample} of {n_total} docs x "
                    f"{n_dense}+{n_sparse} fields, Q={Q}, median of {steps}; extrapolated per-doc-linearly x{scale:.1f}"),
         "exhaustive_value": Q / (t_ex * scale), "ms_per_step_sample": t_step * 1e3, "n_sample": n_sample,
+        "os_cpu_count": os.cpu_count(), "cpu_model": cpu_model(),
     }, t_step * scale
 
 
@@ -220,7 +234,11 @@ def main():
     config = {"workload": f"{args.workload}: {n_total} docs x {n_dense} dense + {n_sparse} sparse fields x {DIM}-d bf16, "
                           f"exhaustive hybrid top-{TOPK}, query-conditioned mixture",
               "n_docs": n_total, "n_dense": n_dense, "n_sparse": n_sparse, "dim": DIM, "batch": Q, "top_k": TOPK,
-              "sharding": f"doc-range x{world}", "cache": "corpus shard >> 126 MB L2 (inputs larger than L2)"}
+              "sharding": f"doc-range x{world}"}
+    shard_mb = (n_total // world) * max(n_dense, 1) * DIM * 2 / 1e6
+    config["cache"] = (f"corpus shard {shard_mb:.0f} MB >> 126 MB L2 (inputs larger than L2)" if shard_mb > 2 * 126 else
+                       f"corpus shard {shard_mb:.0f} MB is NOT larger than the 126 MB L2 and is not flushed between steps: "
+                       "small-workload numbers are L2-assisted")
     bm25_mode = args.sparse_mode == "bm25" and n_sparse > 0
     if n_sparse:
         config["sparse_input"] = ("device BM25: query tokens -> postings scatter-add (mfar_score_topk_bm25)" if bm25_mode
@@ -466,12 +484,14 @@ def main():
         if hbm_bound:
             achieved = a_bytes / (k_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"]}
+                    "frac": achieved / peaks["hbm_gbs"], "frac_of_nominal_peak": achieved / NOMINAL_HBM_GBS,
+                    "nominal_peak": NOMINAL_HBM_GBS}
         else:
             achieved = a_flops / (k_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_tflops_sustained"],
                     "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
+                    "frac_of_nominal_peak": achieved / NOMINAL_BF16_TFLOPS, "nominal_peak": NOMINAL_BF16_TFLOPS,
                     "hbm_gbs_same_launch": a_bytes / (k_ms * 1e-3) / 1e9}
         kname = {"simt": "score_simt_kernel", "tcgen05": "score_tc_kernel", "tcgen05_qs": "score_qs_kernel"}.get(
             args.kernel, "score_qs_kernel" if Q > 64 else "score_tc_kernel")
