@@ -10,7 +10,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "mfar_b200", "libmfar_b200.so")
+OUT = os.environ.get("MFAR_OUT") or os.path.join(HERE, "mfar_b200", "libmfar_b200.so")   # MFAR_OUT: instrumented builds
+BUILD_DIR = os.path.join(HERE, "build" + ("_" + os.path.basename(OUT).replace(".", "_") if os.environ.get("MFAR_OUT") else ""))
 SOURCES = ["capi.cu", "aux_kernels.cu", "score_simt.cu", "score_tc.cu", "score_qs.cu", "bm25.cu", "train.cu", "topk_rows.cu", "sparse_coo.cu"]
 HEADERS = ["common.cuh", "kernels.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "mfar_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -34,9 +35,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(BUILD_DIR, s.replace(".cu", ".o"))
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
