@@ -315,7 +315,7 @@ def main():
             if bm25_mode:
                 sp, ent = None, synth.make_bm25_query_entries(q_count, n_sparse, args.seed + 200 + i).to(device)
             else:
-                sp, ent = synth.make_sparse(q_count, n_sparse, hi - lo, args.seed + 200 + i, device, pitch=8), None
+                sp, ent = synth.make_sparse(q_count, n_sparse, hi - lo, args.seed + 200 + i, device, pitch=64), None
             pool.append((qv, qv.float(), sp, ent))
         return pool
 

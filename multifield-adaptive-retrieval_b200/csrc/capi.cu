@@ -230,12 +230,20 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
 
   const size_t ws_topk = align_up(topk_workspace_bytes(g.lists, g.q_pad_total), 256);
   const int64_t base_ld = int64_t(align_up(size_t(n_docs), kTileDocs));   // tile-wide vector reads stay in bounds
-  const size_t ws_base = n_sparse > 0 ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
+  // Dense [Q,Fs,ld] score rows are gathered and mixed INSIDE the tensor-core scoring epilogues (no [Q,N] intermediate
+  // in HBM) when their rows are 32-byte aligned; COO pairs / BM25 postings scatter into the fp32 base block, and the
+  // SIMT cross-check kernel and the sparse-only row scan read that block too.
+  const bool fuse_sparse = n_sparse > 0 && sp.kind == 1 && n_dense > 0 &&
+                           (g.impl == MFAR_IMPL_TCGEN05 || g.impl == MFAR_IMPL_TCGEN05_QS) &&
+                           sparse_rows_fusable(sp.dense, sp.dense_dtype, sp.dense_ld);
+  const size_t ws_base = (n_sparse > 0 && !fuse_sparse) ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
   const size_t ws_plan = (n_sparse > 0 && sp.kind == 3) ? bm25_plan_bytes(sp.n_entries) : 0;
   if (workspace_bytes < ws_topk + ws_base + ws_plan) return MFAR_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MFAR_ERR_ARG;
 
-  if (n_sparse > 0) {
+  if (fuse_sparse) {
+    a.sparse = sp.dense; a.sparse_dtype = sp.dense_dtype; a.sparse_ld = sp.dense_ld; a.n_sparse = n_sparse;
+  } else if (n_sparse > 0) {
     float* base = reinterpret_cast<float*>(static_cast<char*>(workspace) + ws_topk);
     if (sp.kind == 1) {
       if (int rc = launch_sparse_premix(sp.dense, sp.dense_dtype, sp.dense_ld, n_sparse, w, a.w_ld, n_dense, Q, n_docs,
@@ -453,6 +461,7 @@ int mfar_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields,
 // scratch layout for the host-buffer call
 struct HostScratch {
   size_t off_q, off_qe, off_w, off_sparse, off_scores, off_ids, off_ws, total, ws_bytes;
+  int64_t sparse_ld;
 };
 static HostScratch host_scratch_layout(int Q, int dim, int E, int n_dense, int n_sparse, int64_t n_docs,
                                        int sparse_dtype, int k) {
@@ -461,7 +470,8 @@ static HostScratch host_scratch_layout(int Q, int dim, int E, int n_dense, int n
   h.off_q = o;      o += align_up(size_t(Q) * dim * 2, 256);
   h.off_qe = o;     o += align_up(size_t(Q) * std::max(E, 1) * 4, 256);
   h.off_w = o;      o += align_up(size_t(Q) * (n_dense + n_sparse) * 4, 256);
-  h.off_sparse = o; o += align_up(size_t(Q) * n_sparse * size_t(n_docs) * (sparse_dtype == MFAR_F32 ? 4 : 2), 256);
+  h.sparse_ld = int64_t(align_up(size_t(n_docs), 64));   // 128-/256-byte row pitch: the epilogue gather's vector loads
+  h.off_sparse = o; o += align_up(size_t(Q) * n_sparse * size_t(h.sparse_ld) * (sparse_dtype == MFAR_F32 ? 4 : 2), 256);
   h.off_scores = o; o += align_up(size_t(Q) * k * 4, 256);
   h.off_ids = o;    o += align_up(size_t(Q) * k * 8, 256);
   h.off_ws = o;
@@ -496,10 +506,14 @@ int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int 
     MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_q, q_vecs_host, size_t(Q) * dim * 2, cudaMemcpyHostToDevice, st));
   if (query_cond)
     MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_qe, q_emb_host, size_t(Q) * E * 4, cudaMemcpyHostToDevice, st));
-  if (n_sparse > 0)
-    MFAR_CUDA_OK(cudaMemcpyAsync(s + h.off_sparse, sparse_host,
-                                 size_t(Q) * n_sparse * size_t(n_docs) * (sparse_dtype == MFAR_F32 ? 4 : 2),
-                                 cudaMemcpyHostToDevice, st));
+  if (n_sparse > 0) {                                  // [Q,Fs,N] host rows -> [Q,Fs,sparse_ld] device rows (aligned pitch)
+    const size_t es = sparse_dtype == MFAR_F32 ? 4 : 2;
+    const size_t width = size_t(n_docs) * es, dpitch = size_t(h.sparse_ld) * es;
+    MFAR_CUDA_OK(cudaMemcpy2DAsync(s + h.off_sparse, dpitch, sparse_host, width, width, size_t(Q) * n_sparse,
+                                   cudaMemcpyHostToDevice, st));
+    if (dpitch > width)
+      MFAR_CUDA_OK(cudaMemset2DAsync(s + h.off_sparse + width, dpitch, 0, dpitch - width, size_t(Q) * n_sparse, st));
+  }
   float* w_dev = reinterpret_cast<float*>(s + h.off_w);
   // query_cond == 0: the shared weight row is replicated per query so the scoring kernels index w[q, f] uniformly
   if (int rc = launch_mixture_weights(query_cond ? reinterpret_cast<const float*>(s + h.off_qe) : nullptr, W, mask, Q,
@@ -508,7 +522,7 @@ int mfar_search_host(const void* corpus, int64_t n_docs, int corpus_fields, int 
   float* sc = reinterpret_cast<float*>(s + h.off_scores);
   int64_t* ids = reinterpret_cast<int64_t*>(s + h.off_ids);
   int rc = mfar_score_topk(corpus, n_docs, corpus_fields, field_begin, n_dense, dim, s + h.off_q, Q, w_dev,
-                           n_sparse ? s + h.off_sparse : nullptr, n_sparse, sparse_dtype, n_docs, doc_id_base, k,
+                           n_sparse ? s + h.off_sparse : nullptr, n_sparse, sparse_dtype, h.sparse_ld, doc_id_base, k,
                            nullptr, sc, ids, s + h.off_ws, h.ws_bytes, impl, st);
   if (rc) return rc;
   t_last_launches += 1;

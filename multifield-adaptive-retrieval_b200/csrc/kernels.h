@@ -82,6 +82,12 @@ struct ScoreArgs {
   int w_ld;
   const float* base;        // fp32 [Q, base_ld] pre-mixed sparse contribution or nullptr
   int64_t base_ld;
+  // per-field sparse scores gathered INSIDE the scoring epilogue (tensor-core kernels; dense [Q, n_sparse, sparse_ld]
+  // input with 32-byte aligned rows): acc starts as sum_j w[q, n_dense + j] * sparse[q, j, n].  Exclusive with base.
+  const void* sparse;
+  int sparse_dtype;         // MFAR_F16 / MFAR_F32
+  int64_t sparse_ld;
+  int n_sparse;
   int64_t doc_id_base;
   int k;
 };
@@ -99,6 +105,12 @@ int score_qs_lists_per_worker(int n_dense, int cg);
 // Streaming top-k of the pre-mixed fp32 score rows (sparse-only scorers: no dense field).
 void topk_rows_geometry(int Q, long long n_docs, int* segments, long long* seg_docs);
 int launch_topk_rows(const ScoreArgs& a, void* ws_base, int segments, long long seg_docs, cudaStream_t st);
+// rows of a dense sparse-score tensor can be gathered by the scoring epilogues (32-byte vector loads)
+inline bool sparse_rows_fusable(const void* sparse, int dtype, int64_t ld) {
+  const int es = dtype == MFAR_F32 ? 4 : 2;
+  return sparse != nullptr && (dtype == MFAR_F16 || dtype == MFAR_F32) && (ld * es) % 32 == 0 &&
+         reinterpret_cast<uintptr_t>(sparse) % 32 == 0;
+}
 // Shape envelope of the tcgen05 path.
 bool score_tc_supported(const ScoreArgs& a);
 // geometry chosen for (Q): q_pad per tile, number of q tiles, workers

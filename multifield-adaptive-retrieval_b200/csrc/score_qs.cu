@@ -38,12 +38,15 @@ namespace mfar {
 
 constexpr int kQsThreads = 224;   // ES = 1; ES = 2 adds 4 epilogue warps
 constexpr int kQsEpiBWarp = 7;    // first warp of the second epilogue set
-__host__ __device__ constexpr int qs_threads(int es) { return kQsThreads + (es - 1) * 128; }
+__host__ __device__ constexpr int qs_threads(int es, bool sp = false) { return kQsThreads + (es - 1) * 128 + (sp ? 32 : 0); }
+
 constexpr int kQsIssuerBWarp = 6;   // second MMA-issuing warp (odd units)
 constexpr int kQsQ = 128;        // queries per CTA (TMEM lanes)
 constexpr int kQsDocs = 64;      // docs per unit (UMMA N)
 constexpr int kQsTmemCols = 512;
 constexpr int kQsDCol = 384;     // accumulator columns start here (A occupies [0, dim/2) <= 384)
+constexpr int kSpSlotBytes = 128 * kQsQ;   // one sparse element: 128 queries x 128 bytes (64 f16 / 32 f32 docs)
+constexpr int kSpMaxSlots = 4;
 
 struct QsParams {
   int64_t n_docs;
@@ -55,6 +58,11 @@ struct QsParams {
   int w_ld;
   const float* base;
   int64_t base_ld;
+  const void* sparse;  // [Q, n_sparse, sparse_ld] f16/f32 gathered by the epilogue (exclusive with base), rows 32-B aligned
+  int64_t sparse_ld;
+  int n_sparse;
+  int sparse_f16;
+  int sp_slots;        // sparse ring depth (SP kernels)
   int64_t doc_id_base;
   int k;
   int stages;          // ring depth
@@ -81,9 +89,57 @@ __device__ __forceinline__ void qs_issue_stage(uint32_t d_tmem, uint32_t a0, uin
   }
 }
 
-template <int CG, int ES>
-__global__ void __launch_bounds__(qs_threads(ES), 1)
-score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
+// Sparse term of one query's 64 docs, gathered from the per-field score rows (mfar/data/index.py:111-118: the
+// score_batch gather) and mixed with the query's softmax weights (weighting.py:29) into the same accumulators as the
+// dense fields:  acc[c] += w[q, n_dense + j] * sparse[q, j, doc0 + c] - nothing is written back to HBM.
+//
+// Data path: the [Q, n_sparse, ld] tensor is a 3-D TMA tensor (ld | n_sparse | Q); one ELEMENT = the 128-byte run
+// (64 f16 / 32 f32 docs) of one field for the CTA's 128 queries = a (128 B, 1, 128) box, 16 KB, landing 128-byte
+// swizzled in a small shared-memory ring filled by a dedicated producer warp that runs up to kSpMaxSlots elements
+// ahead.  The epilogue thread of query r reads row r of the slot (8 x LDS.128 with the swizzle XOR - conflict-free,
+// each quarter-warp covers all 32 banks) after each dense field's accumulator drain.  Why TMA and not per-thread
+// global loads: a thread owns one query, so its loads touch one private 128-byte line per field - measured, LDG.256
+// from 128 threads sustains only ~7 GB/s per SM at DRAM latency (the L1 miss path's concurrency), which capped the
+// Amazon-shaped Q=512 kernel at 7.9 ms however deep the register pipeline was (1 or 2 elements ahead, with or
+// without L2 prefetch); the TMA queue is deep enough to keep the 16 KB boxes streaming.
+__device__ __forceinline__ void qs_sparse_consume(const uint8_t* slot, int qloc, bool f16, int e, float wj,
+                                                  float (&acc)[kQsDocs]) {
+  const uint8_t* row = slot + qloc * 128;
+  const int sw = qloc & 7;
+  if (f16) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 v = *reinterpret_cast<const uint4*>(row + ((c ^ sw) << 4));
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w4[x]));
+        acc[c * 8 + 2 * x] = fmaf(wj, f.x, acc[c * 8 + 2 * x]);
+        acc[c * 8 + 2 * x + 1] = fmaf(wj, f.y, acc[c * 8 + 2 * x + 1]);
+      }
+    }
+  } else if ((e & 1) == 0) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ sw) << 4));
+      acc[c * 4 + 0] = fmaf(wj, v.x, acc[c * 4 + 0]); acc[c * 4 + 1] = fmaf(wj, v.y, acc[c * 4 + 1]);
+      acc[c * 4 + 2] = fmaf(wj, v.z, acc[c * 4 + 2]); acc[c * 4 + 3] = fmaf(wj, v.w, acc[c * 4 + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 v = *reinterpret_cast<const float4*>(row + ((c ^ sw) << 4));
+      acc[32 + c * 4 + 0] = fmaf(wj, v.x, acc[32 + c * 4 + 0]); acc[32 + c * 4 + 1] = fmaf(wj, v.y, acc[32 + c * 4 + 1]);
+      acc[32 + c * 4 + 2] = fmaf(wj, v.z, acc[32 + c * 4 + 2]); acc[32 + c * 4 + 3] = fmaf(wj, v.w, acc[32 + c * 4 + 3]);
+    }
+  }
+}
+
+// SP: the epilogue gathers the sparse fields itself (qs_seed_sparse) - a separate instantiation, so the dense-only
+// kernels keep their register allocation
+template <int CG, int ES, bool SP>
+__global__ void __launch_bounds__(qs_threads(ES, SP), 1)
+score_qs_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_sp, QsParams p) {
   constexpr int kRowsPerCta = kQsDocs / CG;               // doc rows this CTA loads per stage
   constexpr int kChunkBytes = kRowsPerCta * kChunkK * 2;  // one [rows x 64] K-major block: 8 KB (CG=1) / 4 KB (CG=2)
   const int kStageBytes = p.kc_per_stage * kChunkBytes;
@@ -91,13 +147,18 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = smem;
-  float* w_s = reinterpret_cast<float*>(smem_b + size_t(p.stages) * kStageBytes);      // [n_dense][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + size_t(p.n_dense) * kQsQ);
+  uint8_t* smem_sp = smem_b + size_t(p.stages) * kStageBytes;                          // [sp_slots][16 KB], 1024-aligned
+  const int sp_slots = SP ? p.sp_slots : 0;
+  float* w_s = reinterpret_cast<float*>(smem_sp + size_t(sp_slots) * kSpSlotBytes);    // [n_dense (+ n_sparse)][128]
+  const int n_w = p.n_dense + (SP ? p.n_sparse : 0);   // weight rows kept in shared memory
+  uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + size_t(n_w) * kQsQ);
   uint64_t* full_bar = bars;                       // [stages]  (leader's are the ones waited on)
   uint64_t* empty_bar = bars + p.stages;           // [stages]
   uint64_t* tfull_bar = bars + 2 * p.stages;       // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]       (leader's are the ones waited on)
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sfull_bar = tempty_bar + 2;            // [kSpMaxSlots] sparse ring: producer warp -> epilogue
+  uint64_t* sempty_bar = sfull_bar + kSpMaxSlots;  // [kSpMaxSlots] epilogue (4 warps of the consuming set) -> producer
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(sempty_bar + kSpMaxSlots);
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
@@ -112,7 +173,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
   int* err = p.ws.err;
 
   // ---- one-time setup
-  for (int i = threadIdx.x; i < p.n_dense * kQsQ; i += qs_threads(ES)) {
+  for (int i = threadIdx.x; i < n_w * kQsQ; i += qs_threads(ES, SP)) {
     const int f = i / kQsQ, c = i % kQsQ;
     w_s[i] = (q0 + c < p.Q) ? p.w[int64_t(q0 + c) * p.w_ld + f] : 0.f;
   }
@@ -120,6 +181,8 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4 * CG); }
+    for (int b = 0; b < kSpMaxSlots; ++b) { mbar_init(&sfull_bar[b], 1); mbar_init(&sempty_bar[b], 4); }
+    if (SP) tma_prefetch_desc(&map_sp);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -172,7 +235,16 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
   if (warp == 0) {
     // ===================================================================== TMA producer (every CTA)
     {                                               // whole warp walks the loop, one elected lane issues
-      int stage = 0; uint32_t phase = 0;
+      // Stage ownership: the two MMA-issuing warps alternate units, and a parity wait on an mbarrier is only sound for
+      // a waiter that observes every phase of that barrier in turn - so each issuer owns HALF of the ring (stages
+      // [b * S, (b + 1) * S) for the issuer of accumulator buffer b) and the producer fills unit u into the half of
+      // issuer u & 1.  (With one shared ring an issuer's first visit to a stage could be for its SECOND fill and pass
+      // the parity test before the first fill had landed: harmless for the 4-stage / 2-per-unit geometry round 1
+      // shipped, where the split happens to coincide with ring order, fatal for others.)
+      const int S_half = p.stages >> 1;
+      int st0 = 0, st1 = 0;                        // next stage inside the half of issuer 0 / 1
+      uint32_t ph0 = 0u, ph1 = 0u;
+      int unit = 0;
       // Query groups (CTA pairs / CTAs with the same blockIdx.y) stream the SAME doc tiles.  They are kept within
       // one sync interval (a half-tile of >= 8 fields) of each other through per-group progress counters so that the second reader of a tile
       // hits L2 instead of HBM (ncu before: DRAM read 1.8x the corpus at Q=512).  Bounded spin: a group that is
@@ -204,7 +276,11 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           for (int f = 0; f < p.n_dense; ++f) {
             const int row0 = (t * p.corpus_fields + p.field_begin + f) * kTileDocs + h * kQsDocs +
                              int(cta_rank) * kRowsPerCta;
+            const int ib = unit & 1;                // issuer (= accumulator buffer) of this unit
+            ++unit;
             for (int s = 0; s < stages_per_unit; ++s) {
+              const int stage = ib ? S_half + st1 : st0;
+              const uint32_t phase = ib ? ph1 : ph0;
               mbar_wait(&empty_bar[stage], phase ^ 1, err, 11);
               if (elect_one()) {
                 if (CG == 2) {
@@ -218,9 +294,38 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
                 }
               }
               __syncwarp();
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              if (ib) { if (++st1 == S_half) { st1 = 0; ph1 ^= 1u; } }
+              else { if (++st0 == S_half) { st0 = 0; ph0 ^= 1u; } }
             }
           }
+        }
+      }
+    }
+  } else if (SP && warp == qs_threads(ES) / 32) {
+    // ===================================================================== sparse producer (last warp, every CTA)
+    // elements in the order the epilogue sets consume them: ES = 1: (tile, half, element); ES = 2: (tile, element,
+    // half) - the two sets then own the even / odd slots of the ring
+    const int n_elems = p.n_sparse * (p.sparse_f16 ? 1 : 2);
+    const int per_elem_docs = p.sparse_f16 ? 64 : 32;
+    int seq = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int64_t tile_doc0 = int64_t(g + i * G) * kTileDocs;
+      for (int a = 0; a < (ES == 2 ? n_elems : 2); ++a) {
+        for (int b = 0; b < (ES == 2 ? 2 : n_elems); ++b) {
+          const int h = ES == 2 ? b : a, e = ES == 2 ? a : b;
+          const int64_t doc0 = tile_doc0 + h * kQsDocs;
+          if (doc0 < p.n_docs) {                     // (the epilogue skips a half-tile past the last doc too)
+            const int slot = seq % sp_slots;
+            mbar_wait(&sempty_bar[slot], ((seq / sp_slots) & 1) ^ 1, err, 16);
+            if (elect_one()) {
+              mbar_expect_tx(&sfull_bar[slot], kSpSlotBytes);
+              const int j = p.sparse_f16 ? e : (e >> 1);
+              const int64_t d = doc0 + (p.sparse_f16 ? 0 : (e & 1) * per_elem_docs);
+              tma_load_3d(&map_sp, &sfull_bar[slot], smem_sp + size_t(slot) * kSpSlotBytes, int(d), j, q0);
+            }
+            __syncwarp();
+          }
+          ++seq;
         }
       }
     }
@@ -247,9 +352,10 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         QS_TICK(t_tempty)
         tc_fence_after();
         for (int s = 0; s < stages_per_unit; ++s) {
-          const int ring = u * stages_per_unit + s;   // position in the producer's stage sequence
-          const int stage = ring % p.stages;
-          const uint32_t phase = uint32_t(ring / p.stages) & 1u;
+          const int ring = (u >> 1) * stages_per_unit + s;   // position in this issuer's half of the ring
+          const int S_half = p.stages >> 1;
+          const int stage = buf * S_half + ring % S_half;
+          const uint32_t phase = uint32_t(ring / S_half) & 1u;
           mbar_wait(&full_bar[stage], phase, err, 14);
           QS_TICK(t_full)
           tc_fence_after();
@@ -293,6 +399,19 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
     const int refresh_mask = p.n_dense >= 8 ? 0 : (p.n_dense >= 4 ? 1 : (p.n_dense >= 2 ? 3 : 7));
     float acc[kQsDocs];
     int u = 0;
+    // fused sparse gather (SP): position of this epilogue set in the sparse ring (see the producer warp)
+    const int sp_elems = SP ? p.n_sparse * (p.sparse_f16 ? 1 : 2) : 0;
+    int sp_seq = (ES == 2) ? eset : 0;               // ES = 2: set s consumes elements s, s + 2, ...
+    auto sp_step = [&](int sp_e, float (&acc_)[kQsDocs]) {
+      const int slot = sp_seq % sp_slots;
+      mbar_wait(&sfull_bar[slot], (sp_seq / sp_slots) & 1, err, 17);
+      const int j = p.sparse_f16 ? sp_e : (sp_e >> 1);
+      qs_sparse_consume(smem_sp + size_t(slot) * kSpSlotBytes, qloc, p.sparse_f16 != 0, sp_e,
+                        w_s[(p.n_dense + j) * kQsQ + qloc], acc_);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty_bar[slot]);
+      sp_seq += ES;
+    };
 #ifdef MFAR_QS_TIMING
     long long e_wait = 0, e_drain = 0, e_push = 0, e_compact = 0, e_prev = clock64();
     int n_compact = 0;
@@ -308,7 +427,12 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
         const int64_t doc0 = int64_t(t) * kTileDocs + h * kQsDocs;
         // accumulators start from the pre-mixed sparse term (16 x 16-byte loads per query row, issued ahead of the
         // wait for the half-tile's first accumulator; base_ld is a multiple of 128, so the row read stays in bounds)
-        if (my_base != nullptr && q_valid && doc0 < p.n_docs) {
+        const bool sp_live = SP && doc0 < p.n_docs;   // warp-uniform: padding queries read TMA zero fill
+        int sp_e = 0;                                // next sparse element of this half-tile to consume
+        if (sp_live) {
+#pragma unroll
+          for (int c = 0; c < kQsDocs; ++c) acc[c] = 0.f;
+        } else if (my_base != nullptr && q_valid && doc0 < p.n_docs) {
           const float4* b4 = reinterpret_cast<const float4*>(my_base + doc0);
 #pragma unroll
           for (int c = 0; c < kQsDocs; c += 4) {
@@ -326,22 +450,26 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, QsParams p) {
           tc_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t(lane_grp * 32) << 16) + uint32_t(kQsDCol + buf * kQsDocs);
           const float wf = w_s[f * kQsQ + qloc];
-          // drain the whole accumulator into registers and hand the TMEM buffer back BEFORE the FMAs: the
-          // release -> next MMA chain (cross-CTA in pair mode) is what bounds the unit rate, not the arithmetic
-          uint32_t v[kQsDocs];
+          {
+            // drain the whole accumulator into registers and hand the TMEM buffer back BEFORE the FMAs: the
+            // release -> next MMA chain (cross-CTA in pair mode) is what bounds the unit rate, not the arithmetic
+            uint32_t v[kQsDocs];
 #pragma unroll
-          for (int c0 = 0; c0 < kQsDocs; c0 += 16)
-            tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {                           // one arrival per epilogue warp frees the accumulator buffer
-            if (CG == 2) mbar_arrive_cluster_rank0(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
+            for (int c0 = 0; c0 < kQsDocs; c0 += 16)
+              tmem_ld16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&v[c0]));
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {                         // one arrival per epilogue warp frees the accumulator buffer
+              if (CG == 2) mbar_arrive_cluster_rank0(&tempty_bar[buf]); else mbar_arrive(&tempty_bar[buf]);
+            }
+#pragma unroll
+            for (int c = 0; c < kQsDocs; ++c) acc[c] = fmaf(wf, __uint_as_float(v[c]), acc[c]);
           }
-#pragma unroll
-          for (int c = 0; c < kQsDocs; ++c) acc[c] = fmaf(wf, __uint_as_float(v[c]), acc[c]);
+          if (sp_live && sp_e < sp_elems) { sp_step(sp_e, acc); ++sp_e; }   // one sparse element per dense field
           QS_ETICK(e_drain)
         }
+        while (sp_live && sp_e < sp_elems) { sp_step(sp_e, acc); ++sp_e; }  // more sparse elements than dense fields
         // ---- 64 docs scored under every field: threshold filter, push
         // adopt the best threshold any CTA found for this query - an L2 round trip, so not more often than once
         // per ~8 MMA units (every half-tile when n_dense >= 8, every 8th for a single_ scorer)
@@ -445,15 +573,16 @@ void score_qs_geometry(int Q, int n_tiles, int* q_tiles, int* workers, int* cg) 
   *q_tiles = qt; *workers = w; *cg = c;
 }
 
-static size_t qs_smem_bytes(int n_dense, int stages, int stage_bytes) {
-  return 1024 + size_t(stages) * stage_bytes + size_t(n_dense) * kQsQ * 4 + (2 * stages + 4) * 8 + 16;
+static size_t qs_smem_bytes(int n_weights, int stages, int stage_bytes, int sp_slots) {
+  return 1024 + size_t(stages) * stage_bytes + size_t(sp_slots) * kSpSlotBytes + size_t(n_weights) * kQsQ * 4 +
+         (2 * stages + 4 + 2 * kSpMaxSlots) * 8 + 16;
 }
 
 // two epilogue sets only where the epilogue is the bound: single-field scorers in CTA-pair mode (Q > 128); at
 // Q <= 128 the kernel is HBM-bound and the extra warps measured ~3 % slower
 int score_qs_lists_per_worker(int n_dense, int cg) { return (n_dense == 1 && cg == 2) ? 2 : 1; }
 
-template <int CG, int ES>
+template <int CG, int ES, bool SP>
 static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, cudaStream_t st) {
   constexpr int kChunkBytes = (kQsDocs / CG) * kChunkK * 2;
   QsParams p;
@@ -461,26 +590,52 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   p.n_dense = a.n_dense; p.k_chunks = a.dim / kChunkK; p.q_vecs = static_cast<const __nv_bfloat16*>(a.q_vecs);
   p.dim = a.dim; p.Q = a.Q; p.w = a.w; p.w_ld = a.w_ld; p.base = a.base; p.base_ld = a.base_ld;
   p.doc_id_base = a.doc_id_base; p.k = a.k;
+  p.sparse = a.sparse; p.sparse_ld = a.sparse_ld; p.n_sparse = a.sparse ? a.n_sparse : 0;
+  p.sparse_f16 = a.sparse_dtype == MFAR_F16;
+  if (a.sparse && (a.base || !sparse_rows_fusable(a.sparse, a.sparse_dtype, a.sparse_ld))) return MFAR_ERR_ARG;
+  const int n_w = a.n_dense + p.n_sparse;
   p.ws = carve_workspace(ws_base, workers * ES, q_tiles * kQsQ);   // ES candidate lists per (CTA, query)
   const size_t smem_cap = 227 * 1024;
-  int kc = 1;                                       // largest divisor of k_chunks with a stage <= 48 KB
+  // Shared memory: corpus ring + (SP) sparse ring of 16 KB slots + weights + barriers.  The corpus ring is split in two
+  // halves, one per MMA-issuing warp (see the producer), so `stages` is even.  Dense-only: stages of up to 48 KB, 192 KB
+  // of ring.  SP: stages of up to 24 KB so that three per issuer fit next to the sparse ring.
+  const int stage_cap = SP ? 24 * 1024 : 48 * 1024;
+  int kc = 1;                                       // largest divisor of k_chunks within the stage cap
   for (int d = 1; d <= p.k_chunks; ++d)
-    if (p.k_chunks % d == 0 && d * kChunkBytes <= 48 * 1024) kc = d;
+    if (p.k_chunks % d == 0 && d * kChunkBytes <= stage_cap) kc = d;
   p.kc_per_stage = kc;
   const int kStageBytes = kc * kChunkBytes;
-  int stages = (192 * 1024) / kStageBytes;
-  while (stages > 2 && qs_smem_bytes(a.n_dense, stages, kStageBytes) > smem_cap) --stages;
+  auto max_stages = [&](int slots) {                // largest even stage count that fits with `slots` sparse slots
+    int st = int((192 * 1024) / kStageBytes) & ~1;
+    while (st > 2 && qs_smem_bytes(n_w, st, kStageBytes, slots) > smem_cap) st -= 2;
+    return st < 2 ? 2 : st;
+  };
+  int sp_slots = 0;
+  if (SP) {                                         // deepest sparse ring that still leaves >= 3 corpus stages per issuer
+    sp_slots = kSpMaxSlots;
+    while (sp_slots > 2 && max_stages(sp_slots) * kStageBytes < 6 * 24 * 1024 &&
+           max_stages(sp_slots - (ES == 2 ? 2 : 1)) > max_stages(sp_slots))
+      sp_slots -= (ES == 2 ? 2 : 1);                // ES = 2: the two epilogue sets own the even / odd slots
+  }
+  const int stages = max_stages(sp_slots);
   p.stages = stages;
-  const size_t smem = qs_smem_bytes(a.n_dense, stages, kStageBytes);
+  p.sp_slots = sp_slots;
+  const size_t smem = qs_smem_bytes(n_w, stages, kStageBytes, sp_slots);
   if (smem > smem_cap) return MFAR_ERR_SHAPE;
 
   CUtensorMap map_b;
   int rc = make_tensor_map_kchunked(&map_b, a.corpus, uint64_t(a.n_tiles) * a.corpus_fields * kTileDocs, a.dim,
                                     kQsDocs / CG, kc, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) return rc;
+  CUtensorMap map_sp = map_b;                       // unused by the dense-only kernels
+  if (SP) {
+    rc = make_tensor_map_sparse_rows(&map_sp, a.sparse, a.sparse_dtype == MFAR_F16, uint64_t(a.sparse_ld),
+                                     uint32_t(a.n_sparse), uint64_t(a.Q), kQsQ);
+    if (rc) return rc;
+  }
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    MFAR_CUDA_OK(cudaFuncSetAttribute(score_qs_kernel<CG, ES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MFAR_CUDA_OK(cudaFuncSetAttribute(score_qs_kernel<CG, ES, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(smem_cap)));
     attr_set = true;
   }
@@ -488,7 +643,7 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(q_tiles, workers);
-  cfg.blockDim = dim3(qs_threads(ES));
+  cfg.blockDim = dim3(qs_threads(ES, SP));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -496,15 +651,21 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MFAR_CUDA_OK(cudaLaunchKernelEx(&cfg, score_qs_kernel<CG, ES>, map_b, p));
+  MFAR_CUDA_OK(cudaLaunchKernelEx(&cfg, score_qs_kernel<CG, ES, SP>, map_b, map_sp, p));
   return MFAR_OK;
 }
 
 int launch_score_qs(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int cg, cudaStream_t st) {
   if (!score_qs_supported(a)) return MFAR_ERR_SHAPE;
-  if (score_qs_lists_per_worker(a.n_dense, cg) == 2) return launch_qs_impl<2, 2>(a, ws_base, workers, q_tiles, st);
-  if (cg == 2) return launch_qs_impl<2, 1>(a, ws_base, workers, q_tiles, st);
-  return launch_qs_impl<1, 1>(a, ws_base, workers, q_tiles, st);
+  const bool sp = a.sparse != nullptr;
+  if (score_qs_lists_per_worker(a.n_dense, cg) == 2)
+    return sp ? launch_qs_impl<2, 2, true>(a, ws_base, workers, q_tiles, st)
+              : launch_qs_impl<2, 2, false>(a, ws_base, workers, q_tiles, st);
+  if (cg == 2)
+    return sp ? launch_qs_impl<2, 1, true>(a, ws_base, workers, q_tiles, st)
+              : launch_qs_impl<2, 1, false>(a, ws_base, workers, q_tiles, st);
+  return sp ? launch_qs_impl<1, 1, true>(a, ws_base, workers, q_tiles, st)
+            : launch_qs_impl<1, 1, false>(a, ws_base, workers, q_tiles, st);
 }
 
 }  // namespace mfar

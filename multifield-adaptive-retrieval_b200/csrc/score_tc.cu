@@ -40,16 +40,104 @@ struct TcParams {
   int w_ld;
   const float* base;
   int64_t base_ld;
+  const void* sparse;   // [Q, n_sparse, sparse_ld] f16/f32 gathered by the epilogue (exclusive with base), rows 32-B aligned
+  int64_t sparse_ld;
+  int n_sparse;
+  int sparse_f16;
   int64_t doc_id_base;
   int k;
   int stages;
   TopkWorkspace ws;
 };
 
+// Sparse term of one corpus tile for the CTA's QP queries, gathered from the per-field score rows (index.py:111-118)
+// and mixed (weighting.py:29) into a shared-memory block base_s[QP][128 docs] fp32 that seeds the accumulators:
+//   base_s[c][n] = sum_j w[q0 + c, n_dense + j] * sparse[q0 + c, j, tile*128 + n]     (j ascending, fmaf)
+// An epilogue THREAD of this kernel owns a doc (TMEM lane), but the score rows run along docs per (query, field) - so
+// the gather has its own mapping and its own two STAGER WARPS (6, 7): a thread takes (query c, 32-byte group g)
+// pairs, 8 lanes cover one query's 128 docs (256 contiguous bytes of f16), a warp four queries; loads of field j+1 are
+// in flight while field j is mixed.  The stagers run one tile ahead of the epilogue (base_full / base_empty
+// mbarriers; the epilogue copies base_s into its accumulators at tile start and hands the block back), so the DRAM
+// latency of the gather never sits in front of an accumulator drain (done by the epilogue warps themselves it cost
+// 17 % at Amazon-shaped Q=64).  The [Q, N] pre-mix block of round 1 (written to and re-read from HBM) is gone.
+constexpr int kStagerThreads = 64;
+constexpr int kStagerWarp0 = 6;
+template <int QP, bool F16>
+__device__ __forceinline__ void tc_stage_sparse(float* base_s, const TcParams& p, int q0, int nq, int64_t tile_doc0,
+                                                const float* w_sp, int et) {   // et: 0 .. kStagerThreads-1
+  constexpr int kEs = F16 ? 2 : 4;
+  constexpr int kLoadDocs = 32 / kEs;               // 16 / 8 docs per 32-byte load
+  constexpr int kGroups = kTileDocs / kLoadDocs;    // 8 / 16 groups per query row
+  constexpr int kPairs = QP * kGroups / kStagerThreads;   // (query, group) pairs per thread: QP/8 (f16), QP/4 (f32)
+  static_assert(kPairs >= 1, "tile too small");
+  constexpr int kBatch = kPairs < 4 ? kPairs : 4;   // pairs processed together (loads in flight: 2 * kBatch)
+  const int64_t row_bytes = p.sparse_ld * kEs;
+  for (int b0 = 0; b0 < kPairs; b0 += kBatch) {
+    const char* src[kBatch];
+    bool live[kBatch];
+    int cq[kBatch], gq[kBatch];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      const int pid = (b0 + i) * kStagerThreads + et;
+      cq[i] = pid / kGroups; gq[i] = pid % kGroups;
+      const int64_t d = tile_doc0 + gq[i] * kLoadDocs;
+      live[i] = cq[i] < nq && d < p.sparse_ld;
+      src[i] = static_cast<const char*>(p.sparse) + (int64_t(q0 + cq[i]) * p.n_sparse * p.sparse_ld + d) * kEs;
+    }
+    float acc[kBatch][kLoadDocs];
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i)
+#pragma unroll
+      for (int e = 0; e < kLoadDocs; ++e) acc[i][e] = 0.f;
+    uint32_t cur[kBatch][8], nxt[kBatch][8];
+    auto load = [&](uint32_t (&b)[kBatch][8], int j) {
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        if (live[i]) {
+          ldg256_stream(src[i] + int64_t(j) * row_bytes, b[i]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) b[i][e] = 0u;
+        }
+      }
+    };
+    load(cur, 0);
+#pragma unroll 2
+    for (int j = 0; j < p.n_sparse; ++j) {
+      if (j + 1 < p.n_sparse) load(nxt, j + 1);
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i) {
+        const float wj = w_sp[j * QP + cq[i]];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (F16) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&cur[i][e]));
+            acc[i][2 * e] = fmaf(wj, f.x, acc[i][2 * e]);
+            acc[i][2 * e + 1] = fmaf(wj, f.y, acc[i][2 * e + 1]);
+          } else {
+            acc[i][e] = fmaf(wj, __uint_as_float(cur[i][e]), acc[i][e]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < kBatch; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) cur[i][e] = nxt[i][e];
+    }
+#pragma unroll
+    for (int i = 0; i < kBatch; ++i) {
+      float4* dst = reinterpret_cast<float4*>(base_s + cq[i] * kTileDocs + gq[i] * kLoadDocs);
+#pragma unroll
+      for (int e = 0; e < kLoadDocs; e += 4) dst[e / 4] = make_float4(acc[i][e], acc[i][e + 1], acc[i][e + 2], acc[i][e + 3]);
+    }
+  }
+}
+
+
 // ------------------------------------------------------------------------------------ the kernel
 // QP: query columns per CTA (UMMA N), one of 16 / 32 / 64.
-template <int QP>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int QP, bool SP>   // SP: sparse fields gathered in-kernel (tc_stage_sparse, 2 more warps); separate instantiation
+__global__ void __launch_bounds__(SP ? kTcThreads + kStagerThreads : kTcThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B resident][w_s][thr as float][thr][cnt][flags][barriers][tmem ptr]
@@ -58,17 +146,22 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint8_t* smem_b = smem_a + size_t(p.stages) * kABytes;
   const int b_chunk_bytes = QP * kChunkK * 2;
   float* w_s = reinterpret_cast<float*>(smem_b + size_t(p.k_chunks) * b_chunk_bytes);     // [n_dense][QP]
-  float* s_thrf = w_s + size_t(p.n_dense) * QP;    // [QP] score of s_thr (float pre-filter), +inf for padding queries
+  float* s_thrf = w_s + size_t(p.n_dense + (SP ? p.n_sparse : 0)) * QP;    // [QP] score of s_thr (float pre-filter), +inf for padding queries
   unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(s_thrf + QP);
   int* s_cnt = reinterpret_cast<int*>(s_thr + QP);
   int* s_flags = s_cnt + QP;                       // reserved (keeps the shared-memory layout)
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_flags + QP) + 7) & ~uintptr_t(7));
+  float* base_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_flags + QP) + 15) & ~uintptr_t(15));   // [QP][128]
+  const int n_w = p.n_dense + (SP ? p.n_sparse : 0);   // weight rows kept in shared memory
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      (reinterpret_cast<uintptr_t>(base_s + (SP ? QP * kTileDocs : 0)) + 7) & ~uintptr_t(7));
   uint64_t* full_bar = bars;                       // [stages]
   uint64_t* empty_bar = bars + p.stages;           // [stages]
   uint64_t* tfull_bar = bars + 2 * p.stages;       // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint64_t* bq_bar = tempty_bar + 2;               // [1]
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bq_bar + 1);
+  uint64_t* base_full = bq_bar + 1;                // [1]  stagers -> epilogue: base_s holds the next tile's sparse term
+  uint64_t* base_empty = base_full + 1;            // [1]  epilogue -> stagers: base_s has been copied out
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(base_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0);   // warp-uniform for the compiler too
   const int lane = threadIdx.x & 31;
@@ -79,7 +172,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   constexpr uint32_t kTmemCols = (2 * QP < 32) ? 32 : 2 * QP;
 
   // ---- one-time setup
-  for (int i = threadIdx.x; i < p.n_dense * QP; i += kTcThreads) {
+  for (int i = threadIdx.x; i < n_w * QP; i += int(blockDim.x)) {
     const int f = i / QP, c = i % QP;
     w_s[i] = (c < nq) ? p.w[int64_t(q0 + c) * p.w_ld + f] : 0.f;
   }
@@ -93,6 +186,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], kEpiThreads); }
     mbar_init(bq_bar, 1);
+    mbar_init(base_full, kStagerThreads);
+    mbar_init(base_empty, kEpiThreads);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr_s, kTmemCols); tmem_relinquish(); }
@@ -161,6 +256,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         __syncwarp();
       }
     }
+  } else if (SP && warp >= kStagerWarp0) {
+    // ===================================================================== sparse stagers (warps 6, 7)
+    const int st = int(threadIdx.x) - kStagerWarp0 * 32;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int64_t tile_doc0 = int64_t(g + i * int(gridDim.x)) * kTileDocs;
+      mbar_wait(base_empty, (i & 1) ^ 1, err, 6);
+      if (p.sparse_f16) tc_stage_sparse<QP, true>(base_s, p, q0, nq, tile_doc0, w_s + p.n_dense * QP, st);
+      else tc_stage_sparse<QP, false>(base_s, p, q0, nq, tile_doc0, w_s + p.n_dense * QP, st);
+      mbar_arrive(base_full);                        // release: this thread's base_s stores
+    }
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int lane_grp = warp & 3;                 // TMEM lanes 32*lane_grp .. +31 are this warp's
@@ -182,7 +287,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       // 32 docs) are issued here, ahead of the wait for the tile's first accumulator, instead of serialising with
       // the push loop after the last field.
       const int64_t doc_local = int64_t(t) * kTileDocs + doc_in_tile;
-      if (p.base != nullptr && doc_local < p.n_docs) {
+      if (SP) {
+        mbar_wait(base_full, i & 1, err, 7);
+#pragma unroll
+        for (int c = 0; c < QP; ++c) acc[c] = base_s[c * kTileDocs + doc_in_tile];
+        mbar_arrive(base_empty);                     // the stagers may fill base_s for the next tile
+      } else if (p.base != nullptr && doc_local < p.n_docs) {
         const float* bp = p.base + int64_t(q0) * p.base_ld + doc_local;
 #pragma unroll
         for (int c = 0; c < QP; ++c) acc[c] = (c < nq) ? __ldg(bp + int64_t(c) * p.base_ld) : 0.f;
@@ -294,24 +404,28 @@ void score_tc_geometry(int Q, int n_tiles, int* q_pad, int* q_tiles, int* worker
   *q_pad = qp; *q_tiles = qt; *workers = w;
 }
 
-static size_t tc_smem_bytes(int qp, int n_dense, int k_chunks, int stages) {
-  return 1024 + size_t(stages) * kABytes + size_t(k_chunks) * qp * kChunkK * 2 + size_t(n_dense) * qp * 4 +
-         size_t(qp) * 20 + 8 + (2 * stages + 5) * 8 + 16;
+static size_t tc_smem_bytes(int qp, int n_weights, bool sparse, int k_chunks, int stages) {
+  return 1024 + size_t(stages) * kABytes + size_t(k_chunks) * qp * kChunkK * 2 + size_t(n_weights) * qp * 4 +
+         size_t(qp) * 20 + 16 + (sparse ? size_t(qp) * kTileDocs * 4 : 0) + 8 + (2 * stages + 7) * 8 + 16;
 }
 
-template <int QP>
+template <int QP, bool SP>
 static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, cudaStream_t st) {
   TcParams p;
   p.n_docs = a.n_docs; p.n_tiles = a.n_tiles; p.corpus_fields = a.corpus_fields; p.field_begin = a.field_begin;
   p.n_dense = a.n_dense; p.k_chunks = a.dim / kChunkK; p.Q = a.Q; p.w = a.w; p.w_ld = a.w_ld; p.base = a.base;
   p.base_ld = a.base_ld; p.doc_id_base = a.doc_id_base; p.k = a.k;
+  p.sparse = a.sparse; p.sparse_ld = a.sparse_ld; p.n_sparse = a.sparse ? a.n_sparse : 0;
+  p.sparse_f16 = a.sparse_dtype == MFAR_F16;
+  if (a.sparse && (a.base || !sparse_rows_fusable(a.sparse, a.sparse_dtype, a.sparse_ld))) return MFAR_ERR_ARG;
+  const int n_w = a.n_dense + p.n_sparse;
   p.ws = carve_workspace(ws_base, workers, q_tiles * QP);
   int stages = 8;
   const size_t smem_cap = 227 * 1024;
-  while (stages > 2 && tc_smem_bytes(QP, a.n_dense, p.k_chunks, stages) > smem_cap) --stages;
-  if (tc_smem_bytes(QP, a.n_dense, p.k_chunks, stages) > smem_cap) return MFAR_ERR_SHAPE;
+  while (stages > 2 && tc_smem_bytes(QP, n_w, a.sparse != nullptr, p.k_chunks, stages) > smem_cap) --stages;
+  if (tc_smem_bytes(QP, n_w, a.sparse != nullptr, p.k_chunks, stages) > smem_cap) return MFAR_ERR_SHAPE;
   p.stages = stages;
-  const size_t smem = tc_smem_bytes(QP, a.n_dense, p.k_chunks, stages);
+  const size_t smem = tc_smem_bytes(QP, n_w, a.sparse != nullptr, p.k_chunks, stages);
 
   CUtensorMap map_a, map_b;
   int rc = make_tensor_map_2d(&map_a, a.corpus, uint64_t(a.n_tiles) * a.corpus_fields * kTileDocs, a.dim, kTileDocs,
@@ -322,12 +436,12 @@ static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
 
   static bool attr_set = false;   // per template instantiation
   if (!attr_set) {
-    MFAR_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<QP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
+    MFAR_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<QP, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
     attr_set = true;
   }
   MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));   // shared thresholds
   dim3 grid(workers, q_tiles);
-  score_tc_kernel<QP><<<grid, kTcThreads, smem, st>>>(map_a, map_b, p);
+  score_tc_kernel<QP, SP><<<grid, SP ? kTcThreads + kStagerThreads : kTcThreads, smem, st>>>(map_a, map_b, p);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }
@@ -335,9 +449,12 @@ static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
 int launch_score_tc(const ScoreArgs& a, void* ws_base, int workers, int q_tiles, int q_pad, cudaStream_t st) {
   if (!score_tc_supported(a)) return MFAR_ERR_SHAPE;
   switch (q_pad) {
-    case 16: return launch_tc_impl<16>(a, ws_base, workers, q_tiles, st);
-    case 32: return launch_tc_impl<32>(a, ws_base, workers, q_tiles, st);
-    case 64: return launch_tc_impl<64>(a, ws_base, workers, q_tiles, st);
+    case 16: return a.sparse ? launch_tc_impl<16, true>(a, ws_base, workers, q_tiles, st)
+                             : launch_tc_impl<16, false>(a, ws_base, workers, q_tiles, st);
+    case 32: return a.sparse ? launch_tc_impl<32, true>(a, ws_base, workers, q_tiles, st)
+                             : launch_tc_impl<32, false>(a, ws_base, workers, q_tiles, st);
+    case 64: return a.sparse ? launch_tc_impl<64, true>(a, ws_base, workers, q_tiles, st)
+                             : launch_tc_impl<64, false>(a, ws_base, workers, q_tiles, st);
     default: return MFAR_ERR_SHAPE;
   }
 }

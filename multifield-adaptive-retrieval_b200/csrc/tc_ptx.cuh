@@ -10,7 +10,11 @@ namespace mfar {
 constexpr int kChunkK = 64;   // bf16 elements per K-chunk = 128 B = swizzle span
 constexpr int kUmmaK = 16;
 constexpr int kEpiThreads = 128;   // 4 epilogue warps: one per 32-lane TMEM sub-partition
-constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;  // ~2 s: turn a pipeline bug into a trap, not a hang
+#ifdef MFAR_TIMEOUT_EXIT
+constexpr unsigned long long kWaitTimeoutCycles = 200000000ull;
+#else
+constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;
+#endif  // ~2 s: turn a pipeline bug into a trap, not a hang
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -38,6 +42,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   const unsigned long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > kWaitTimeoutCycles) {
+#ifdef MFAR_TIMEOUT_EXIT   // debug build: report and leave instead of trapping (a trap loses the printf buffer)
+      if ((threadIdx.x & 31) == 0)
+        printf("[mfar_b200] mbarrier wait timed out: code %d, block (%d,%d), warp %d, parity %u\n", code, int(blockIdx.x),
+               int(blockIdx.y), int(threadIdx.x >> 5), parity);
+      asm volatile("exit;");
+#endif
       if (err) atomicExch(err, code);
       __threadfence_system();
       asm volatile("trap;");
@@ -74,6 +84,14 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// 32-byte global load (LDG.E.256, sm_100+), read-only path, no L1 allocation: used where a thread streams a private
+// row (one query's sparse scores) and every 32-byte sector is consumed exactly once
+__device__ __forceinline__ void ldg256_stream(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -283,6 +301,29 @@ static inline int make_tensor_map_kchunked(CUtensorMap* map, const void* base, u
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "[mfar_b200] cuTensorMapEncodeTiled (k-chunked) failed: %d\n", int(r));
+    return MFAR_ERR_CUDA;
+  }
+  return MFAR_OK;
+}
+
+
+// 3-D view of a [Q, n_sparse, ld] f16/f32 score tensor: dims (ld | n_sparse | Q), box = (128 bytes of docs, 1 field,
+// box_q queries), 128-byte swizzled: the rows of one field for a tile of queries, one row per 128-byte line.
+// Out-of-range docs / queries are zero-filled by the TMA unit.  Needs a 16-byte aligned base and row pitch.
+static inline int make_tensor_map_sparse_rows(CUtensorMap* map, const void* base, bool f16, uint64_t ld,
+                                              uint32_t n_sparse, uint64_t Q, uint32_t box_q) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return MFAR_ERR_CUDA;
+  const uint64_t es = f16 ? 2 : 4;
+  cuuint64_t gdim[3] = {ld, n_sparse, Q};
+  cuuint64_t gstride[2] = {ld * es, ld * es * n_sparse};
+  cuuint32_t box[3] = {cuuint32_t(128 / es), 1, box_q};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[mfar_b200] cuTensorMapEncodeTiled (sparse rows) failed: %d\n", int(r));
     return MFAR_ERR_CUDA;
   }
   return MFAR_OK;

@@ -263,8 +263,9 @@ class MultiFieldRetriever:
         q_vecs [Q,dim]: query vectors for the dense dots (rounded to bf16);
         q_emb  [Q,E]  : fp32 query embedding for the mixture softmax (defaults to q_vecs, as in the
                         reference where both come from the same encoder, contrastive.py:688-694);
-        sparse [Q,Fs,ld>=N]: precomputed per-field BM25 scores of this shard's docs (f16/f32); a row pitch ``ld``
-                        that is a multiple of 8 lets the f16 pre-mix kernel use 16-byte loads.
+        sparse [Q,Fs,ld>=N]: precomputed per-field BM25 scores of this shard's docs (f16/f32).  With a 32-byte aligned row
+                        pitch (``ld`` a multiple of 16 for f16, 8 for f32) the rows are gathered and mixed INSIDE the
+                        scoring epilogue; otherwise a pre-mix kernel writes a [Q,N] fp32 block first.
         sparse_coo     : instead of ``sparse``: (keys int32 [nnz,2] = (query row, GLOBAL doc row), vals f16/f32 [nnz],
                         field_offsets [Fs+1]) on the device - the reference's precomputed-BM25 layout
                         (``PrecomputedSparseScores.batch``); pairs that are absent score 0 (index.py:120-125).
@@ -602,7 +603,7 @@ class GraphedSearch:
         self.q_emb = torch.zeros((self.Q, E), dtype=torch.float32, device=dev) if E else None
         self.sparse = self.entries = None
         if sparse == "dense":
-            ld = sparse_ld or _round_up(r.n_docs, 8)
+            ld = sparse_ld or _round_up(r.n_docs, 64)     # 32-byte aligned rows: gathered inside the scoring epilogue
             self.sparse = torch.zeros((self.Q, r.n_sparse, ld), dtype=sparse_dtype, device=dev)
         elif sparse == "bm25":
             if r.bm25 is None or max_entries <= 0:

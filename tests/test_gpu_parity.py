@@ -305,7 +305,40 @@ def test_search_host_equals_device_search_and_counts_launches():
     s_h, i_h = r.search_host(qh, q.float().pin_memory(), sp.pin_memory())
     assert not s_h.is_cuda
     assert torch.equal(s_h, s_dev.cpu()) and torch.equal(i_h, i_dev.cpu())
-    assert r.last_launches == 4                         # + mixture weights
+    assert r.last_launches == 3                         # mixture weights + scoring (sparse gathered in its epilogue) + merge
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_qs", "auto"])
+@pytest.mark.parametrize("shape", [(71, 1111, 768, 8, 8, 3), (72, 3001, 256, 1, 2, 257), (73, 2000, 768, 22, 22, 64),
+                                   (74, 129, 64, 2, 1, 17), (75, 5000, 128, 3, 5, 140), (76, 640, 64, 2, 3, 40)],
+                         ids=lambda s: f"s{s[0]}")
+def test_sparse_gather_fused_into_the_scoring_epilogue(shape, impl):
+    """north_star (2): sparse score rows with a 32-byte aligned pitch are gathered and mixed inside the scoring
+    epilogue - no pre-mix launch, no [Q,N] block (index.py:111-118 + contrastive.py:681-686 in one pass).  f16 and f32
+    rows, ragged tails, single-field two-epilogue-set variant; agrees with the pre-mix path (unaligned pitch)."""
+    seed, N, d, Fd, Fs, Q = shape
+    fields, q, sp, W = synth(seed, N, d, Fd, Fs, Q, True)
+    r = build(fields, W, True, Fs, 100, impl=impl)
+    r.mask_field([Fd])                                   # a masked sparse field
+    mask = torch.ones(Fd + Fs, 1)
+    mask[Fd] = 0
+    ref = O.exhaustive_scores(q, fields, sp.float(), O.mixture_weights(q, W, True), mask)
+    ld = (N + 63) // 64 * 64
+    qd = q.to(DEV)
+    n_u = N if N % 16 else N + 1                         # a pitch that is NOT 32-byte aligned -> pre-mix kernel + base block
+    unaligned = torch.zeros((Q, Fs, n_u), dtype=torch.float16, device=DEV)
+    unaligned[:, :, :N] = sp.to(DEV)
+    s0, i0 = r.search(qd, qd, unaligned)
+    assert r.last_launches == 3                          # pre-mix + scoring + merge
+    for dtype in (torch.float16, torch.float32):
+        padded = torch.zeros((Q, Fs, ld), dtype=dtype, device=DEV)
+        padded[:, :, :N] = sp.to(DEV)
+        s1, i1 = r.search(qd, qd, padded)
+        assert r.last_launches == 2                      # scoring + merge
+        assert_topk_parity(s1.cpu().numpy(), i1.cpu().numpy(), ref.numpy(), 100)
+        # same result as the pre-mix path up to fp32 summation order (the query-stationary epilogue interleaves the
+        # sparse and dense terms)
+        assert_same_topk_up_to_ties(s1.cpu(), i1.cpu(), s0.cpu(), i0.cpu())
 
 
 @pytest.mark.parametrize("impl", IMPLS)
@@ -315,14 +348,19 @@ def test_virtual_shards_merge_equals_single_shard(impl):
     from mfar_b200.dist import merge_keys, shard_range
     fields, q, sp, W = synth(41, 4000, 768, 3, 1, 5, True)
     k = 100
+
+    def pitched(x):                                  # 128-byte row pitch: every shard takes the fused sparse gather
+        out = torch.zeros((x.shape[0], x.shape[1], (x.shape[2] + 63) // 64 * 64), dtype=x.dtype, device=DEV)
+        out[:, :, :x.shape[2]] = x
+        return out
     full = build(fields, W, True, 1, k, impl=impl)
-    s0, i0, k0 = full.search(q.to(DEV), q.to(DEV), sp.to(DEV), return_keys=True)
+    s0, i0, k0 = full.search(q.to(DEV), q.to(DEV), pitched(sp), return_keys=True)
     for R in (2, 4, 8):
         keys = []
         for rank in range(R):
             lo, hi = shard_range(4000, rank, R)
             sh = build([f[lo:hi] for f in fields], W, True, 1, k, doc_id_base=lo, impl=impl)
-            _, _, kk = sh.search(q.to(DEV), q.to(DEV), sp[:, :, lo:hi].contiguous().to(DEV), return_keys=True)
+            _, _, kk = sh.search(q.to(DEV), q.to(DEV), pitched(sp[:, :, lo:hi]), return_keys=True)
             keys.append(kk)
         s, i = merge_keys(torch.stack(keys), k)
         assert torch.equal(i, i0) and torch.equal(s, s0), R

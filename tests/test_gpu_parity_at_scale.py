@@ -51,7 +51,7 @@ def _free():
 
 def _make_sparse(Q, Fs, n, seed):
     from mfar_b200 import synth as S
-    ld = (n + 7) // 8 * 8
+    ld = (n + 63) // 64 * 64                       # 128-byte rows: gathered inside the scoring epilogue
     out = torch.zeros((Q, Fs, ld), dtype=torch.float16, device=DEV)
     for q0 in range(0, Q, 32):                     # bounded temporaries (fp32 [32,Fs,N] x 4)
         q1 = min(Q, q0 + 32)
