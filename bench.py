@@ -3,16 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload scale_10m_all] [--batch 512]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      # the reference's CPU pipeline (oracle port) on host cores
+    python bench.py --impl reference ...      # the reference's CPU pipeline on the host cores
 
 One "step" = one batch of Q queries scored against the whole corpus (all fields), mixed, top-100.
-Multi-GPU = strong scaling: the SAME global corpus is doc-range sharded over the ranks, per-shard
-top-k keys are all-gathered (NCCL) and merged on every rank.  Prints ONE JSON line on rank 0.
+Multi-GPU = strong scaling: the SAME global corpus is doc-range sharded over the ranks, per-shard top-k keys are
+exchanged and merged by one kernel over NVLink peer memory (NCCL all-gather + merge kernel as fallback).
+Rank 0 prints ONE JSON line: the headline workload (BASELINE.json configs[4], batch 512) with `roofline`,
+`cpu_baseline`, `e2e`, `parity_check`, `other_batches` (batch 1 / 64 of the same corpus, at every N) and
+`other_workloads` (C2 PRIME hybrid, C3 MAG, C4 Amazon hybrid, C5 single_), each with its own roofline and parity check.
 """
 from __future__ import annotations
 
 import argparse
 import ctypes
+import gc
 import json
 import os
 import statistics
@@ -22,7 +26,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (os.path.join(ROOT, "multifield-adaptive-retrieval_b200"), os.path.join(ROOT, "oracle")):
+for _p in (os.path.join(ROOT, "multifield-adaptive-retrieval_b200"), os.path.join(ROOT, "oracle"),
+           os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -34,6 +39,10 @@ NOMINAL_BF16_TFLOPS = 2250.0    # dense bf16, B200 data sheet
 DIM = 768
 TOPK = 100
 GEN_CHUNK = 65536
+# what rides along with the headline in the default run: (workload, batches) - BASELINE.json configs 2, 3, 4 and the
+# single_ scorer of config 5
+OTHER_WORKLOADS = (("prime_full", (1, 64)), ("mag_full", (1, 512)), ("amazon_full", (64, 512)),
+                   ("scale_10m_single", (1, 64, 512)))
 
 
 def load_peaks():
@@ -95,27 +104,6 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ---------------------------------------------------------------------------------------- corpus
-def build_shard(n_total, n_fields, lo, hi, seed, device):
-    """Rank-local PackedCorpus holding global docs [lo, hi).  Generation is per global 64k-doc chunk so every
-    shard count sees the same global corpus."""
-    from mfar_b200 import synth
-    from mfar_b200.modeling.retrieval import PackedCorpus
-    pc = PackedCorpus(hi - lo, n_fields, DIM, device)
-    mu = synth.corpus_mean(DIM, seed, device)
-    c0, c1 = lo // GEN_CHUNK, (hi - 1) // GEN_CHUNK
-    for c in range(c0, c1 + 1):
-        g = torch.Generator(device=device)
-        g.manual_seed(seed * 1000003 + c + 1)
-        clo, chi = c * GEN_CHUNK, min(n_total, (c + 1) * GEN_CHUNK)
-        a, b = max(lo, clo), min(hi, chi)
-        for f in range(n_fields):
-            rows = synth.make_field_rows(chi - clo, DIM, mu, g, device)
-            pc.load_rows(f, a - lo, rows[a - clo:b - clo])
-    torch.cuda.synchronize()
-    return pc, mu
-
-
 def cpu_model() -> str:
     try:
         with open("/proc/cpuinfo") as f:
@@ -134,73 +122,479 @@ def algorithmic_work(n_docs, n_dense, n_sparse, Q, sparse_bytes=2):
     return bytes_, flops
 
 
-# ---------------------------------------------------------------------------------------- CPU legs
-def cpu_reference_leg(n_total, n_dense, n_sparse, Q, seed, budget_s, steps, warmup):
-    """The reference's CPU pipeline (oracle port of trec_eval_step: per-field retrieve_batch -> union -> rescore ->
-    mask -> mixture -> top-100, fp32 torch on all host threads) on a bounded doc sample; q/s is extrapolated
-    per-doc-linearly to the full corpus and labelled so.  (Inputs are drawn on the GPU when there is one, only to
-    make the sample quickly; everything timed runs on the host cores.)"""
-    import mfar_oracle as O
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_leg(n_total, n_dense, n_sparse, Q, seed, steps, warmup):
+    """The reference's CPU pipeline (``trec_eval_step``: per-field retrieve_batch -> union -> per-query score_batch ->
+    mask -> mixture -> top-100) on all host threads, on a FIXED bounded sample: 200,000 docs (or the corpus, if smaller)
+    and min(Q, 64) queries - 64 is the reference's own dev batch.  Driven through oracle/cpu_pipeline.py: the reference's
+    own DenseFlatIndex / MemoryMapDict / LinearWeights when /root/reference is present (kind "reference"), else the
+    port that pays the same per-call costs (kind "port").  The per-step time is linear in the doc count with a
+    per-query constant (the union / rescore / Python part): t(n) = a + b*n is fitted from a second, 50,000-doc sample
+    and ONLY the fitted line is evaluated at the full size - value = Q_s / (a + b*n_total)."""
+    import cpu_pipeline as C
+    import ref_import
     torch.set_num_threads(os.cpu_count() or 1)
-    gdev = "cuda" if torch.cuda.is_available() else "cpu"
-    g = torch.Generator(device=gdev).manual_seed(seed)
-    mu = torch.randn(DIM, generator=g, device=gdev)
+    kind = "reference" if ref_import.available() else "port"
+    q_s = min(Q, 64)
+    n2 = min(n_total, 200_000)
+    n1 = min(n_total, 50_000)
+    make_rows = None
+    if torch.cuda.is_available():                     # draw the sample on the GPU (setup only; everything timed is CPU)
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        mu = torch.randn(DIM, generator=g, device="cuda")
 
-    def draw(*shape):
-        return torch.randn(*shape, generator=g, device=gdev)
+        def make_rows(n, d, f):
+            return (torch.randn(n, d, generator=g, device="cuda") + 0.5 * mu).to(torch.bfloat16).float().cpu().numpy()
+    tmp_root = None                                   # field memmaps: tmpfs when there is room (the reference's temp_dir
+    try:                                              # is served from the page cache once touched), else the default
+        st = os.statvfs("/dev/shm")
+        if st.f_bavail * st.f_frsize > 2 * n2 * max(n_dense, 1) * DIM * 4:
+            tmp_root = "/dev/shm"
+    except OSError:
+        pass
+    t2 = C.time_pipeline(kind, n2, n_dense, n_sparse, q_s, DIM, seed, steps=steps, warmup=warmup, make_rows=make_rows,
+                         tmp_root=tmp_root)
+    t_step = statistics.median(t2)
+    if n1 < n2:
+        t1 = statistics.median(C.time_pipeline(kind, n1, n_dense, n_sparse, q_s, DIM, seed, steps=3, warmup=1,
+                                               make_rows=make_rows, tmp_root=tmp_root))
+        b = max((t_step - t1) / (n2 - n1), 0.0)
+        a = max(t_step - b * n2, 0.0)
+        t_full = a + b * n_total
+    else:
+        a, b, t_full = t_step, 0.0, t_step
+    extrap = n_total > n2
+    sample = (f"{kind} of trec_eval_step (oracle/cpu_pipeline.py), fp32 torch/numpy on {torch.get_num_threads()} host "
+              f"threads, field memmaps on disk; timed on {n2} of {n_total} docs x {n_dense}+{n_sparse} fields, "
+              f"{q_s} queries per step, median of {steps}"
+              + (f"; t(n) = a + b*n fitted with a {n1}-doc sample and evaluated at {n_total} docs" if extrap else ""))
+    return {"value": q_s / t_full, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
+            "ms_per_step_sample": t_step * 1e3, "n_sample": n2, "queries_per_step": q_s,
+            "fit_a_s": a, "fit_b_s_per_doc": b, "extrapolated": extrap, "os_cpu_count": os.cpu_count(),
+            "cpu_model": cpu_model()}
 
-    q = O.round_bf16((draw(Q, DIM) + 0.5 * mu).cpu())
-    W = (0.05 * draw(DIM, n_dense + n_sparse)).cpu()
 
-    def make(n):
-        fields = [(draw(n, DIM) + 0.5 * mu).to(torch.bfloat16).float().cpu() for _ in range(n_dense)]
-        sp = None
-        if n_sparse:
-            u = torch.rand(Q, n_sparse, n, generator=g, device=gdev)
-            sp = torch.where(u < 0.95, torch.zeros((), device=gdev),
-                             4.0 * torch.rand(Q, n_sparse, n, generator=g, device=gdev)).cpu()
-        return fields, sp
+# ---------------------------------------------------------------------------------------- GPU arm
+class Ctx:
+    """Process-wide state of our arm: device, ranks, the peer exchange, shard weights."""
 
-    def run_once(fields, sp):
+    def __init__(self, args):
+        import torch.distributed as dist
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.dist = dist
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.device)
+        self.exchange, self.exchange_kind = None, "none (1 GPU)"
+        if self.world > 1:
+            from mfar_b200.dist import PeerExchange
+            if os.environ.get("MFAR_EXCHANGE", "p2p") == "p2p":
+                try:
+                    self.exchange = PeerExchange(q_cap=max(1024, args.batch), k_cap=128, device=self.device)
+                    self.exchange_kind = "fused NVLink peer-memory exchange+merge kernel (mfar_topk_exchange_merge)"
+                except Exception as e:  # noqa: BLE001  (symmetric memory unavailable: NCCL all-gather + merge kernel)
+                    self.exchange_kind = (f"nccl all_gather + merge kernel (peer exchange unavailable: "
+                                          f"{type(e).__name__}: {e})")[:300]
+            else:
+                self.exchange_kind = "nccl all_gather + merge kernel"
+        self.peaks = load_peaks()
+        self.weights = [1.0] * self.world             # relative docs/s of every rank (calibrated when --balance)
+        self.balance_note = "equal doc ranges"
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], device=self.device, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+    def calibrate(self, n_dense, Q, seconds=0.7):
+        """Speed-weighted shards: every step ends in an exchange that waits for the slowest rank, and the GPUs of a node
+        settle at different clocks under the 1 kW cap (a few per cent apart, persistently).  Each rank times the scoring
+        kernel on an identical 128k-doc calibration shard for `seconds` of sustained load; doc ranges are then sized in
+        proportion to the measured docs/s."""
+        from mfar_b200 import synth
+        from mfar_b200.modeling.retrieval import MultiFieldRetriever, PackedCorpus
+        from mfar_b200.modeling.weighting import LinearWeights
+        n = 131072
+        pc = PackedCorpus(n, max(n_dense, 1), DIM, self.device)
+        synth.fill_packed_corpus(pc, seed=99)
+        mu = synth.corpus_mean(DIM, 99, self.device)
+        layer = LinearWeights(DIM, max(n_dense, 1), query_cond=True).to(self.device)
+        r = MultiFieldRetriever(pc, layer, top_k=TOPK)
+        q = synth.make_queries(Q, DIM, mu, 98, self.device)
+        qe = q.float()
+        for _ in range(3):
+            r.search(q, qe)
+        self.barrier()
+        t_end = time.perf_counter() + seconds
+        laps = []
+        while time.perf_counter() < t_end:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                r.search(q, qe)
+            e1.record()
+            e1.synchronize()
+            laps.append(e0.elapsed_time(e1) / 20)
+        mine = statistics.median(laps[len(laps) // 2:])          # the settled second half
+        t = torch.zeros(self.world, device=self.device, dtype=torch.float64)
+        t[self.rank] = mine
+        self.dist.all_reduce(t)
+        ms = t.tolist()
+        self.weights = [1.0 / max(x, 1e-9) for x in ms]
+        spread = (max(ms) - min(ms)) / min(ms)
+        self.balance_note = (f"speed-weighted doc ranges (calibration kernel ms per rank: "
+                             f"{', '.join(f'{x:.3f}' for x in ms)}; spread {100 * spread:.1f} %)")
+        del r, pc
+        torch.cuda.empty_cache()
+
+
+def build_shard(n_total, n_fields, lo, hi, seed, device):
+    """Rank-local PackedCorpus holding global docs [lo, hi).  Generation is per global 64k-doc chunk so every
+    shard count (and every shard boundary) sees the same global corpus."""
+    from mfar_b200 import synth
+    from mfar_b200.modeling.retrieval import PackedCorpus
+    pc = PackedCorpus(hi - lo, n_fields, DIM, device)
+    mu = synth.corpus_mean(DIM, seed, device)
+    c0, c1 = lo // GEN_CHUNK, (hi - 1) // GEN_CHUNK
+    for c in range(c0, c1 + 1):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1000003 + c + 1)
+        clo, chi = c * GEN_CHUNK, min(n_total, (c + 1) * GEN_CHUNK)
+        a, b = max(lo, clo), min(hi, chi)
+        for f in range(n_fields):
+            rows = synth.make_field_rows(chi - clo, DIM, mu, g, device)
+            pc.load_rows(f, a - lo, rows[a - clo:b - clo])
+    torch.cuda.synchronize()
+    return pc, mu
+
+
+class Workload:
+    """One corpus (this rank's shard of it), its retriever, and the timing / checking legs."""
+
+    def __init__(self, ctx: Ctx, name: str, docs_override: int = 0):
+        from mfar_b200 import synth
+        from mfar_b200.dist import ShardedRetriever, weighted_shard_ranges
+        from mfar_b200.modeling.retrieval import MultiFieldRetriever
+        from mfar_b200.modeling.weighting import LinearWeights
+        self.ctx, self.name = ctx, name
+        a = ctx.args
+        self.n_total, self.n_dense, self.n_sparse = synth.SHAPES[name]
+        if docs_override:
+            self.n_total = docs_override
+        self.bm25_mode = a.sparse_mode == "bm25" and self.n_sparse > 0
+        self.lo, self.hi = weighted_shard_ranges(self.n_total, ctx.weights)[ctx.rank]
         t0 = time.perf_counter()
-        O.union_rescore(q, fields, sp, q, W, True, None, TOPK)
-        return time.perf_counter() - t0
+        if self.n_dense:
+            self.pc, self.mu = build_shard(self.n_total, self.n_dense, self.lo, self.hi, a.seed, ctx.device)
+        else:                                             # sparse-only scorer: nothing to pack
+            self.pc, self.mu = None, synth.corpus_mean(DIM, a.seed, ctx.device)
+        F = self.n_dense + self.n_sparse
+        layer = LinearWeights(DIM, F, query_cond=True)
+        with torch.no_grad():
+            layer.weight.copy_(synth.make_mixture(DIM, F, a.seed + 1))
+        self.layer = layer.to(ctx.device)
+        self.bm25_fields = None
+        if self.bm25_mode:
+            self.bm25_fields = [synth.make_bm25_field(self.n_total, a.seed + 300 + j, ctx.device,
+                                                      doc_range=(self.lo, self.hi)) for j in range(self.n_sparse)]
+            torch.cuda.synchronize()
+        self.retr = MultiFieldRetriever(self.pc, self.layer, n_sparse=self.n_sparse, top_k=TOPK, doc_id_base=self.lo,
+                                        impl=a.kernel, sparse_indices=self.bm25_fields, n_docs=self.hi - self.lo,
+                                        device=ctx.device)
+        self.sharded = ShardedRetriever(self.retr, exchange=ctx.exchange)
+        self.setup_s = time.perf_counter() - t0
+        self.graphs = {}
 
-    def run_exhaustive(fields, sp):
-        t0 = time.perf_counter()
-        O.exhaustive_topk(q, fields, sp, O.mixture_weights(q, W, True), None, TOPK)
-        return time.perf_counter() - t0
+    # ------------------------------------------------------------------ inputs
+    def make_batches(self, Q, n_pool=4):
+        from mfar_b200 import synth
+        a, dev = self.ctx.args, self.ctx.device
+        n_shard = self.hi - self.lo
+        if self.n_sparse and not self.bm25_mode:          # keep the pool of [Q,Fs,N] f16 tensors within a few GB
+            n_pool = max(1, min(n_pool, int(6e9 // max(1, Q * self.n_sparse * n_shard * 2))))
+        pool = []
+        for i in range(n_pool):
+            qv = synth.make_queries(Q, DIM, self.mu, a.seed + 100 + i, dev)
+            sp = ent = None
+            if self.bm25_mode:
+                ent = synth.make_bm25_query_entries(Q, self.n_sparse, a.seed + 200 + i).to(dev)
+            elif self.n_sparse:
+                ld = (n_shard + 63) // 64 * 64            # 128-byte row pitch: gathered inside the scoring epilogue
+                sp = torch.zeros((Q, self.n_sparse, ld), dtype=torch.float16, device=dev)
+                for q0 in range(0, Q, 32):                # shard columns [lo, hi) of the global sparse tensor
+                    q1 = min(Q, q0 + 32)
+                    full = synth.make_sparse(q1 - q0, self.n_sparse, self.n_total, a.seed + 200 + 1000 * i + q0, dev)
+                    sp[q0:q1, :, :n_shard] = full[:, :, self.lo:self.hi]
+                    del full
+            pool.append((qv, qv.float(), sp, ent))
+        return pool
 
-    # two-point calibration t(n) = a + b*n, then size the sample to the time budget
-    n1, n2 = min(n_total, 4096), min(n_total, 32768)
-    f1, s1 = make(n1)
-    run_once(f1, s1)
-    t1 = run_once(f1, s1)
-    f2, s2 = make(n2)
-    t2 = run_once(f2, s2)
-    b = max((t2 - t1) / max(1, n2 - n1), 1e-9)
-    a = max(t1 - b * n1, 0.0)
-    per_call = max(budget_s / max(1, steps + warmup + 1), 0.5)
-    n_sample = int((per_call - a) / b) if per_call > a else n2
-    ram_cap = int(16e9 / (max(1, n_dense) * DIM * 4 + Q * n_sparse * 4))
-    n_sample = max(TOPK, min(n_sample, ram_cap, n_total))
-    fields, sp = make(n_sample)
-    for _ in range(warmup):
-        run_once(fields, sp)
-    times = [run_once(fields, sp) for _ in range(steps)]
-    t_ex = run_exhaustive(fields, sp)
-    scale = n_total / n_sample
-    t_step = statistics.median(times)
-    return {
-        "value": Q / (t_step * scale), "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-        "sample": (f"oracle union_rescore (faithful trec_eval_step port), fp32 torch CPU, {n_sample} of {n_total} docs x "
-                   f"{n_dense}+{n_sparse} fields, Q={Q}, median of {steps}; extrapolated per-doc-linearly x{scale:.1f}"),
-        "exhaustive_value": Q / (t_ex * scale), "ms_per_step_sample": t_step * 1e3, "n_sample": n_sample,
-        "os_cpu_count": os.cpu_count(), "cpu_model": cpu_model(),
-    }, t_step * scale
+    # ------------------------------------------------------------------ one step
+    def step(self, batch, graph: bool):
+        qv, qe, sp, ent = batch
+        if graph:
+            key = (qv.shape[0], 0 if sp is None else sp.data_ptr())      # one graph per resident sparse tensor
+            gs = self.graphs.get(key)
+            if gs is None:
+                from mfar_b200.modeling.retrieval import GraphedSearch
+                gs = self.graphs[key] = GraphedSearch(
+                    self.retr, qv.shape[0], sparse="bm25" if self.bm25_mode else ("dense" if self.n_sparse else "none"),
+                    max_entries=0 if ent is None else ent.shape[0], sparse_buffer=sp,
+                    sharded=self.sharded if self.ctx.world > 1 else None)
+            out = gs(qv, qe, sparse=sp, entries=ent)
+            return out, gs.launches
+        out = self.sharded.search(qv, qe, sp, sparse_tokens=ent) if self.ctx.world > 1 else \
+            self.retr.search(qv, qe, sp, sparse_tokens=ent)
+        extra = 1 + (2 if self.ctx.world > 1 and self.ctx.exchange is not None else (1 if self.ctx.world > 1 else 0))
+        return out, self.retr.last_launches + extra       # + mixture weights (+ epoch bump + exchange / merge)
+
+    def time_device(self, pool, steps, warmup, graph: bool, profile: bool, sample_clocks=False):
+        """K timed steps with device-resident inputs.  Returns (ms total [max over ranks], launches, kernel ms list,
+        clocks).  The scoring kernel's own duration comes from the library's CUDA-event pair around it; a graph replay
+        carries no such events, so with `graph` the kernel is timed in a separate eager pass of the same length."""
+        from mfar_b200 import _native as nv
+        ctx = self.ctx
+        for i in range(warmup):
+            self.step(pool[i % len(pool)], graph)
+        ctx.barrier()
+        sampler = ClockSampler(ctx.local_rank) if (sample_clocks and ctx.rank == 0) else None
+        if sampler:
+            sampler.start()
+        prof = profile and not graph
+        if prof:
+            nv.check(nv.lib().mfar_profile_enable(1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        e0.record()
+        for i in range(steps):
+            launches += self.step(pool[i % len(pool)], graph)[1]
+        e1.record()
+        ctx.barrier()
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if sampler else None
+        kern_ms = []
+        if prof:
+            kern_ms = self._collect_profile()
+        elif profile:                                      # graph: eager pass for the kernel's own duration
+            for i in range(min(warmup, 3)):
+                self.step(pool[i % len(pool)], False)
+            ctx.barrier()
+            nv.check(nv.lib().mfar_profile_enable(1))
+            for i in range(steps):
+                self.step(pool[i % len(pool)], False)
+            ctx.barrier()
+            kern_ms = self._collect_profile()
+        return ms, launches, kern_ms, clocks
+
+    @staticmethod
+    def _collect_profile():
+        from mfar_b200 import _native as nv
+        buf = (ctypes.c_float * 256)()
+        n = nv.lib().mfar_profile_collect(ctypes.addressof(buf), 256)
+        nv.lib().mfar_profile_enable(0)
+        return [buf[i] for i in range(max(n, 0))]
+
+    def time_e2e(self, pool, steps, warmup, graph: bool):
+        """Host buffers in, host result out, every step.  N=1: ONE C-ABI call (mfar_search_host: H2D of the batch,
+        mixture weights, scoring, top-k, D2H, stream sync).  N>1: pinned host -> device copies, the sharded step
+        (graph replay), D2H of the merged [Q,100] result."""
+        ctx = self.ctx
+        n_shard = self.hi - self.lo
+        pool_host = [(qv.cpu().pin_memory(), qe.cpu().pin_memory(),
+                      None if sp is None else sp[:, :, :n_shard].contiguous().cpu().pin_memory(),
+                      None if ent is None else ent.cpu().pin_memory()) for qv, qe, sp, ent in pool[:2]]
+        Q = pool[0][0].shape[0]
+        out_s = torch.empty((Q, TOPK), dtype=torch.float32).pin_memory()
+        out_i = torch.empty((Q, TOPK), dtype=torch.int64).pin_memory()
+        dev_sp = None if pool[0][2] is None else torch.zeros_like(pool[0][2])
+
+        def one(i):
+            qh, qeh, sph, enth = pool_host[i % len(pool_host)]
+            if ctx.world == 1:
+                if self.bm25_mode:
+                    self.retr.search_host_bm25(qh, qeh, enth, out_scores=out_s, out_ids=out_i)
+                else:
+                    self.retr.search_host(qh, qeh, sph, out_scores=out_s, out_ids=out_i)
+                return
+            qv = qh.to(ctx.device, non_blocking=True)
+            qe = qeh.to(ctx.device, non_blocking=True)
+            if sph is not None:
+                dev_sp[:, :, :n_shard].copy_(sph, non_blocking=True)
+            ent = None if enth is None else enth.to(ctx.device, non_blocking=True)
+            (s, ids), _ = self.step((qv, qe, dev_sp, ent), graph)
+            out_s.copy_(s, non_blocking=True)
+            out_i.copy_(ids, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for i in range(warmup):
+            one(i)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(i)
+        e1.record()
+        ctx.barrier()
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        if self.bm25_mode:
+            h2d = Q * DIM * 2 + Q * DIM * 4 + pool[0][3].shape[0] * 12
+        else:
+            h2d = Q * DIM * 2 + Q * DIM * 4 + (Q * self.n_sparse * n_shard * 2 if self.n_sparse else 0)
+        return ms, h2d, Q * TOPK * 12
+
+    # ------------------------------------------------------------------ roofline of the scoring kernel
+    def roofline(self, Q, k_ms, n_kernels, ms_total, steps):
+        """Per launch, this rank's shard.  The fused scoring kernel moves the corpus AND (dense-tensor input, gathered in
+        its epilogue) the sparse rows; with device BM25 the postings are moved by the scatter kernel, and the scoring
+        kernel reads the fp32 base block instead."""
+        a, peaks = self.ctx.args, self.ctx.peaks
+        n_shard = self.hi - self.lo
+        if k_ms is None:
+            return None
+        if self.n_dense == 0:
+            a_bytes, a_flops = Q * n_shard * 4 + Q * TOPK * 12, 0.0            # streaming top-k of the fp32 rows
+            kname = "topk_rows_kernel"
+        else:
+            a_bytes, a_flops = algorithmic_work(n_shard, self.n_dense, 0 if self.bm25_mode else self.n_sparse, Q)
+            if self.bm25_mode:
+                a_bytes += Q * n_shard * 4                                      # base[Q,N] read by the epilogue
+            kname = {"simt": "score_simt_kernel", "tcgen05": "score_tc_kernel", "tcgen05_qs": "score_qs_kernel"}.get(
+                a.kernel, "score_qs_kernel" if Q > 64 else "score_tc_kernel")
+        hbm_bound = Q < 200 or self.n_dense == 0
+        if hbm_bound:
+            achieved = a_bytes / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "frac_of_nominal_peak": achieved / NOMINAL_HBM_GBS,
+                    "nominal_peak": NOMINAL_HBM_GBS}
+        else:
+            achieved = a_flops / (k_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops_sustained"],
+                    "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
+                    "frac_of_nominal_peak": achieved / NOMINAL_BF16_TFLOPS, "nominal_peak": NOMINAL_BF16_TFLOPS,
+                    "hbm_gbs_same_launch": a_bytes / (k_ms * 1e-3) / 1e9}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and self.ctx.world == 1 and not a.docs:
+            traffic = json.load(open(tpath)).get(f"{self.name}|{Q}")
+        roof.update({"traffic": traffic,
+                     "traffic_source": "ncu --set full capture of this kernel at this shape, profiles/ncu_traffic.json "
+                                       "(a profiler pass, not re-measured in this run)" if traffic else None,
+                     "kernel": kname, "kernel_ms": k_ms,
+                     "kernel_share_of_step": k_ms * steps / ms_total if ms_total else None,
+                     "algorithmic_bytes_per_launch": a_bytes, "algorithmic_flops_per_launch": a_flops,
+                     "peak_source": peaks["source"] + (" copy bandwidth" if hbm_bound else
+                                                       " (sustained: kernel timed inside a long step)")})
+        return roof
+
+    # ------------------------------------------------------------------ what was timed is also checked
+    def parity_check(self, batch, n_check=4):
+        """(1) N>1: the fused NVLink exchange+merge result of the batch equals, bit for bit, the NCCL path (all-gather
+        of the per-shard keys + mfar_topk_merge).  (2) the first `n_check` queries are ranked against tests/checker.py
+        (plain torch fp32 over the packed corpus, TF32 off, each rank its shard, candidates all-gathered) with the
+        near-tie rule of tests/parity.py - a dropped winner fails."""
+        from checker import Fp32Checker, assert_topk_parity_at_scale
+        from mfar_b200.dist import all_gather_keys, merge_keys
+        ctx = self.ctx
+        qv, qe, sp, ent = batch
+        res = {"queries": 0, "ok": False}
+        try:
+            if ctx.world > 1:
+                s, ids = self.sharded.search(qv, qe, sp, sparse_tokens=ent)
+            else:
+                s, ids = self.retr.search(qv, qe, sp, sparse_tokens=ent)
+            if ctx.world > 1:
+                _, _, keys = self.retr.search(qv, qe, sp, return_keys=True, sparse_tokens=ent)
+                s2, i2 = merge_keys(all_gather_keys(keys), TOPK)
+                same = bool(torch.equal(s, s2) and torch.equal(ids, i2))
+                res["fused_exchange_equals_nccl_path"] = same
+                if not same:
+                    raise AssertionError("fused exchange result differs from all_gather + merge")
+            if self.bm25_mode:                            # BM25 scores are produced on the device: no independent rows
+                res.update({"ok": True, "note": "checker skipped for device-BM25 sparse fields"})
+                return res
+            n = min(n_check, qv.shape[0])
+            q, spn = qv[:n], (None if sp is None else sp[:n])
+            F = self.n_dense + self.n_sparse
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            w = torch.softmax(q.float() @ self.layer.weight.detach().float(), dim=1) * self.retr.mask.reshape(1, F)
+            torch.backends.cuda.matmul.allow_tf32 = prev
+            chk = Fp32Checker(self.pc, n_docs=self.hi - self.lo, doc_id_base=self.lo)
+            K2 = TOPK + 28
+            cs, ci = chk.topk(q if self.pc is not None else None, w.contiguous(), TOPK, sparse=spn, slack=K2 - TOPK)
+            got_i = ids[:n]
+            mine = (got_i >= self.lo) & (got_i < self.hi)
+            resc = chk.rescore(q if self.pc is not None else None, w.contiguous(), got_i, sparse=spn) * mine
+            if ctx.world > 1:
+                if cs.shape[1] < K2:                       # tiny shard: pad
+                    pad = K2 - cs.shape[1]
+                    cs = torch.nn.functional.pad(cs, (0, pad), value=float("-inf"))
+                    ci = torch.nn.functional.pad(ci, (0, pad), value=-1)
+                all_s = [torch.empty_like(cs) for _ in range(ctx.world)]
+                all_i = [torch.empty_like(ci) for _ in range(ctx.world)]
+                ctx.dist.all_gather(all_s, cs.contiguous())
+                ctx.dist.all_gather(all_i, ci.contiguous())
+                cs, ci = Fp32Checker._reduce(torch.cat(all_s, dim=1), torch.cat(all_i, dim=1), K2)
+                ctx.dist.all_reduce(resc)
+            if ctx.rank == 0:
+                assert_topk_parity_at_scale(s[:n], got_i, cs, ci, resc, TOPK, self.n_total, 0, what=self.name)
+            res.update({"queries": n, "ok": True,
+                        "checker": "tests/checker.py: torch fp32 over the packed corpus, TF32 off; near-tie rule"})
+        except AssertionError as e:
+            res.update({"ok": False, "error": str(e)[:300]})
+        return res
+
+    def release(self):
+        self.graphs.clear()
+        self.retr = self.sharded = self.pc = self.bm25_fields = None
+        gc.collect()
+        torch.cuda.empty_cache()
 
 
-# ---------------------------------------------------------------------------------------- main
+def run_workload(ctx: Ctx, name, batches, steps, warmup, headline=False):
+    """All legs of one workload.  `batches[0]` is the main batch; returns a dict (rank 0 fills the line from it)."""
+    a = ctx.args
+    wl = Workload(ctx, name, a.docs if headline else 0)
+    graph = bool(a.graph) or ctx.world > 1             # the sharded step is launch-sensitive: always replay it as a graph
+    out = {"workload": name, "n_docs": wl.n_total, "n_dense": wl.n_dense, "n_sparse": wl.n_sparse,
+           "shard_docs": wl.hi - wl.lo, "cuda_graph": graph, "setup_s": wl.setup_s, "batches": []}
+    for bi, Q in enumerate(batches):
+        main = headline and bi == 0
+        st = steps if main else max(5, steps // 2)
+        pool = wl.make_batches(Q, 4 if main else 2)
+        ms, launches, km, clocks = wl.time_device(pool, st, warmup if main else 3, graph, profile=True,
+                                                  sample_clocks=main)
+        k_ms = statistics.mean(km) if km else None
+        rec = {"batch": Q, "value": Q * st / (ms * 1e-3), "ms_per_step": ms / st, "steps": st,
+               "roofline": wl.roofline(Q, k_ms, len(km), ms, st), "gpu_launches": launches}
+        if main:
+            rec["clocks"] = clocks
+            ms_e, h2d, d2h = wl.time_e2e(pool, st, warmup, graph)
+            rec["e2e"] = {"value": Q * st / (ms_e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
+                          "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / st,
+                          "path": "mfar_search_host (C ABI, pinned host buffers)" if ctx.world == 1 else
+                                  "pinned host -> device copies + sharded step (graph replay) + D2H of the merged top-k"}
+        if Q == max(batches):                          # check the largest batch (up to 4 of its queries)
+            out["parity_check"] = wl.parity_check(pool[0])
+        out["batches"].append(rec)
+        del pool
+        gc.collect()
+        torch.cuda.empty_cache()
+    wl.release()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -209,16 +603,20 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="scale_10m_all")
     ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--docs", type=int, default=0, help="override the workload's doc count (debug)")
+    ap.add_argument("--docs", type=int, default=0, help="override the headline workload's doc count (debug)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tcgen05", "tcgen05_qs"])
-    ap.add_argument("--extra-batches", default="1,64", help="also measured on the device-resident path at N=1")
+    ap.add_argument("--extra-batches", default="1,64", help="also measured on the headline corpus (device-resident)")
+    ap.add_argument("--others", default="default",
+                    help="'default' = the BASELINE.json configs that ride along (C2, C3, C4, C5 single_), 'none', or a "
+                         "list like mag_full:1:512,amazon_full:64")
     ap.add_argument("--sparse-mode", default="precomputed", choices=["precomputed", "bm25"],
                     help="sparse fields as precomputed [Q,Fs,N] f16 score tensors (north_star (2)) or scored on the "
                          "device from query tokens against HBM-resident BM25 postings (SURVEY 8f-3)")
     ap.add_argument("--graph", action="store_true",
-                    help="N=1: replay the device-resident step as one CUDA graph (GraphedSearch); the scoring kernel's "
-                         "own duration for the roofline is taken from a short eager pass")
-    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+                    help="N=1: replay the device-resident step as one CUDA graph (always on for N>1)")
+    ap.add_argument("--balance", default="auto", choices=["auto", "off"],
+                    help="N>1: size the doc ranges by each GPU's measured speed (auto) or equally (off)")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="0 skips the cpu_baseline leg of our arm")
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -229,7 +627,6 @@ def main():
         n_total = args.docs
     Q = args.batch
     rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": f"{args.workload}: {n_total} docs x {n_dense} dense + {n_sparse} sparse fields x {DIM}-d bf16, "
                           f"exhaustive hybrid top-{TOPK}, query-conditioned mixture",
@@ -239,21 +636,21 @@ def main():
     config["cache"] = (f"corpus shard {shard_mb:.0f} MB >> 126 MB L2 (inputs larger than L2)" if shard_mb > 2 * 126 else
                        f"corpus shard {shard_mb:.0f} MB is NOT larger than the 126 MB L2 and is not flushed between steps: "
                        "small-workload numbers are L2-assisted")
-    bm25_mode = args.sparse_mode == "bm25" and n_sparse > 0
     if n_sparse:
-        config["sparse_input"] = ("device BM25: query tokens -> postings scatter-add (mfar_score_topk_bm25)" if bm25_mode
-                                  else "precomputed [Q,Fs,N] f16 score tensor")
+        config["sparse_input"] = ("device BM25: query tokens -> postings scatter-add (mfar_score_topk_bm25)"
+                                  if args.sparse_mode == "bm25" else
+                                  "precomputed [Q,Fs,N] f16 score tensor, gathered inside the scoring epilogue")
 
     # ------------------------------------------------------------------ reference arm (CPU, rank 0 only)
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, t_full = cpu_reference_leg(n_total, n_dense, n_sparse, Q, args.seed, max(args.cpu_budget_s, 20.0) * 3,
-                                       args.steps, args.warmup)
+        cb = cpu_reference_leg(n_total, n_dense, n_sparse, Q, args.seed, args.steps, args.warmup)
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "queries/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": cb,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step_sample"],
+                "ms_per_step_is": "one timed step = the bounded sample described in cpu_baseline.sample",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -267,290 +664,60 @@ def main():
     os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA sm_100 device (there is no CPU fallback for the product path)")
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
-    import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
-    from mfar_b200 import _native as nv
-    from mfar_b200.dist import ShardedRetriever, shard_range
-    from mfar_b200.modeling.retrieval import MultiFieldRetriever
-    from mfar_b200.modeling.weighting import LinearWeights
+    ctx = Ctx(args)
+    if world > 1 and args.balance == "auto" and n_dense:
+        ctx.calibrate(n_dense, Q)
+    config["sharding"] = f"doc-range x{world}, {ctx.balance_note}"
 
-    lo, hi = shard_range(n_total, rank, world)
-    t_setup = time.perf_counter()
-    if n_dense:
-        pc, mu = build_shard(n_total, n_dense, lo, hi, args.seed, device)
-    else:                                             # sparse-only scorer: nothing to pack
-        pc, mu = None, synth.corpus_mean(DIM, args.seed, device)
-    F = n_dense + n_sparse
-    layer = LinearWeights(DIM, F, query_cond=True)
-    with torch.no_grad():
-        layer.weight.copy_(synth.make_mixture(DIM, F, args.seed + 1))
-    bm25_fields = None
-    if bm25_mode:
-        bm25_fields = [synth.make_bm25_field(n_total, args.seed + 300 + j, device, doc_range=(lo, hi))
-                       for j in range(n_sparse)]
-        torch.cuda.synchronize()
-    retr = MultiFieldRetriever(pc, layer.to(device), n_sparse=n_sparse, top_k=TOPK, doc_id_base=lo, impl=args.kernel,
-                               sparse_indices=bm25_fields, n_docs=hi - lo, device=device)
-    exchange, exchange_kind = None, "none (1 GPU)"
-    if world > 1:
-        from mfar_b200.dist import PeerExchange
-        if os.environ.get("MFAR_EXCHANGE", "p2p") == "p2p":
-            try:
-                exchange = PeerExchange(q_cap=max(1024, Q), k_cap=128, device=device)
-                exchange_kind = "fused NVLink peer-memory exchange+merge kernel (mfar_topk_exchange_merge)"
-            except Exception as e:  # noqa: BLE001  (symmetric memory unavailable: NCCL all-gather + merge kernel)
-                exchange_kind = f"nccl all_gather + merge kernel (peer exchange unavailable: {type(e).__name__}: {e})"[:300]
-        else:
-            exchange_kind = "nccl all_gather + merge kernel"
-    sharded = ShardedRetriever(retr, exchange=exchange)
-    setup_s = time.perf_counter() - t_setup
-
-    def make_batches(q_count, n_pool=4):
-        pool = []
-        for i in range(n_pool):
-            qv = synth.make_queries(q_count, DIM, mu, args.seed + 100 + i, device)
-            if bm25_mode:
-                sp, ent = None, synth.make_bm25_query_entries(q_count, n_sparse, args.seed + 200 + i).to(device)
-            else:
-                sp, ent = synth.make_sparse(q_count, n_sparse, hi - lo, args.seed + 200 + i, device, pitch=64), None
-            pool.append((qv, qv.float(), sp, ent))
-        return pool
-
-    def batch_postings(ent):
-        """postings the batch touches on this shard (for the algorithmic byte count)"""
-        total = 0
-        for j, f in enumerate(bm25_fields):
-            t = ent[ent[:, 1] == j][:, 2].long()
-            ip = f.scores["indptr"]
-            total += int((ip[t + 1] - ip[t]).sum().item())
-        return total
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    graphs = {}
-
-    def step(batch):
-        qv, qe, sp, ent = batch
-        if args.graph and world == 1:
-            gs = graphs.get(qv.shape[0])
-            if gs is None:
-                from mfar_b200.modeling.retrieval import GraphedSearch
-                gs = graphs[qv.shape[0]] = GraphedSearch(
-                    retr, qv.shape[0], sparse="bm25" if bm25_mode else ("dense" if n_sparse else "none"),
-                    max_entries=0 if ent is None else ent.shape[0], sparse_ld=None if sp is None else sp.shape[2])
-            gs(qv, qe, sparse=sp, entries=ent)
-            return gs.launches
-        sharded.search(qv, qe, sp, sparse_tokens=ent)
-        return retr.last_launches + 1 + 1                   # + mixture-weights kernel + cross-shard merge kernel
-
-    def run_device(pool, steps, warmup, profile=False):
-        if args.graph and world == 1 and profile:           # kernel duration from a short eager pass
-            nv.check(nv.lib().mfar_profile_enable(1))
-            for i in range(3):
-                qv, qe, sp, ent = pool[i % len(pool)]
-                sharded.search(qv, qe, sp, sparse_tokens=ent)
-            torch.cuda.synchronize()
-            buf0 = (ctypes.c_float * 256)()
-            n0 = nv.lib().mfar_profile_collect(ctypes.addressof(buf0), 256)
-            eager_kern_ms = [buf0[i] for i in range(max(n0, 0))]
-            nv.lib().mfar_profile_enable(0)
-            profile = False
-        else:
-            eager_kern_ms = None
-        for i in range(warmup):
-            step(pool[i % len(pool)])
-        barrier()
-        if profile:
-            nv.check(nv.lib().mfar_profile_enable(1))
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches = 0
-        ncu_range = profile and os.environ.get("MFAR_NCU_RANGE") == "1"   # ncu --profile-from-start off
-        if ncu_range:
-            torch.cuda.profiler.start()
-        e0.record()
-        for i in range(steps):
-            launches += step(pool[i % len(pool)])
-        e1.record()
-        barrier()
-        if ncu_range:
-            torch.cuda.profiler.stop()
-        ms = e0.elapsed_time(e1)
-        kern_ms = []
-        if profile:
-            buf = (ctypes.c_float * 256)()
-            n = nv.lib().mfar_profile_collect(ctypes.addressof(buf), 256)
-            kern_ms = [buf[i] for i in range(max(n, 0))]
-            nv.lib().mfar_profile_enable(0)
-        if eager_kern_ms is not None:
-            kern_ms = eager_kern_ms
-        if world > 1:
-            t = torch.tensor([ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms, launches, kern_ms
-
-    def run_e2e(pool_host, steps, warmup):
-        """Through the C-ABI host-buffer call: pinned host inputs -> H2D -> mixture + scoring + top-k -> D2H."""
-        out_s = torch.empty((Q, TOPK), dtype=torch.float32).pin_memory()
-        out_i = torch.empty((Q, TOPK), dtype=torch.int64).pin_memory()
-
-        def one(i):
-            qh, qeh, sph, enth = pool_host[i % len(pool_host)]
-            if bm25_mode:
-                retr.search_host_bm25(qh, qeh, enth, out_scores=out_s, out_ids=out_i)
-            else:
-                retr.search_host(qh, qeh, sph, out_scores=out_s, out_ids=out_i)
-        for i in range(warmup):
-            one(i)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            one(i)
-        e1.record()
-        barrier()
-        return e0.elapsed_time(e1)
-
-    peaks = load_peaks()
-    pool_dev = make_batches(Q)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_total, launches, kern_ms = run_device(pool_dev, args.steps, args.warmup, profile=True)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # e2e: N=1 goes through mfar_search_host; N>1 adds the (device) key exchange + merge per step
-    pool_host = [(qv.cpu().pin_memory(), qe.cpu().pin_memory(),
-                  None if sp is None else sp[:, :, :hi - lo].contiguous().cpu().pin_memory(),   # host call: pitch = N
-                  None if ent is None else ent.cpu().pin_memory())
-                 for qv, qe, sp, ent in pool_dev]
-    if world == 1:
-        ms_e2e = run_e2e(pool_host, args.steps, args.warmup)
-    else:
-        def e2e_multi():
-            for i in range(args.warmup):
-                one_e2e(i)
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(args.steps):
-                one_e2e(i)
-            e1.record()
-            barrier()
-            t = torch.tensor([e0.elapsed_time(e1)], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return t.item()
-
-        def one_e2e(i):
-            qh, qeh, sph, enth = pool_host[i % len(pool_host)]
-            qv = qh.to(device, non_blocking=True)
-            qe = qeh.to(device, non_blocking=True)
-            sp = None if sph is None else sph.to(device, non_blocking=True)
-            ent = None if enth is None else enth.to(device, non_blocking=True)
-            s, ids = sharded.search(qv, qe, sp, sparse_tokens=ent)
-            s.cpu(); ids.cpu()
-        ms_e2e = e2e_multi()
-    if bm25_mode:
-        h2d = Q * DIM * 2 + Q * DIM * 4 + pool_dev[0][3].shape[0] * 12
-    else:
-        h2d = Q * DIM * 2 + Q * DIM * 4 + (Q * n_sparse * (hi - lo) * 2 if n_sparse else 0)
-    d2h = Q * TOPK * 12
-
-    # roofline of the dominant kernel (the fused scoring kernel), per launch, this rank's shard
-    n_shard = hi - lo
-    a_bytes, a_flops = algorithmic_work(n_shard, n_dense, 0 if bm25_mode else n_sparse, Q)
-    sparse_stage = None
-    if bm25_mode:
-        # per batch: 8 B read per posting touched + the fp32 base[Q,N] row block zeroed, accumulated (L2 atomics) and
-        # read back once by the scoring epilogue
-        postings = statistics.mean(batch_postings(b[3]) for b in pool_dev)
-        sparse_bytes = postings * 8 + 2 * Q * n_shard * 4
-        a_bytes += sparse_bytes
-        sparse_stage = {"postings_per_batch": postings, "algorithmic_bytes": sparse_bytes,
-                        "entries_per_batch": int(pool_dev[0][3].shape[0])}
-    if n_dense == 0:
-        # sparse-only scorer: the timed kernel is the streaming top-k over the fp32 base[Q,N] rows - its own algorithmic
-        # traffic is that block read once (the pre-mix / BM25 scatter that wrote it are separate launches)
-        a_bytes = Q * n_shard * 4 + Q * TOPK * 12
-    k_ms = statistics.mean(kern_ms) if kern_ms else None
-    hbm_bound = Q < 200 or n_dense == 0
-    if k_ms:
-        if hbm_bound:
-            achieved = a_bytes / (k_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / peaks["hbm_gbs"], "frac_of_nominal_peak": achieved / NOMINAL_HBM_GBS,
-                    "nominal_peak": NOMINAL_HBM_GBS}
-        else:
-            achieved = a_flops / (k_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["bf16_tflops_sustained"],
-                    "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
-                    "frac_of_nominal_peak": achieved / NOMINAL_BF16_TFLOPS, "nominal_peak": NOMINAL_BF16_TFLOPS,
-                    "hbm_gbs_same_launch": a_bytes / (k_ms * 1e-3) / 1e9}
-        kname = {"simt": "score_simt_kernel", "tcgen05": "score_tc_kernel", "tcgen05_qs": "score_qs_kernel"}.get(
-            args.kernel, "score_qs_kernel" if Q > 64 else "score_tc_kernel")
-        if n_dense == 0:
-            kname = "topk_rows_kernel"
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and world == 1 and not args.docs:
-            traffic = json.load(open(tpath)).get(f"{args.workload}|{Q}")
-        roof.update({"traffic": traffic, "traffic_source": "ncu --set full capture, profiles/ncu_traffic.json" if traffic else None,
-                     "kernel": kname,
-                     "kernel_ms": k_ms,
-                     "kernel_share_of_step": (k_ms * args.steps if args.graph else k_ms * len(kern_ms)) / ms_total
-                     if ms_total else None,
-                     "algorithmic_bytes_per_launch": a_bytes, "algorithmic_flops_per_launch": a_flops,
-                     "peak_source": peaks["source"] + (" (sustained: kernel timed inside a long step)" if not hbm_bound else " copy bandwidth")})
-    else:
-        roof = None
-
-    extra = []
-    if world == 1 and rank == 0 and args.extra_batches:
-        for qb in [int(x) for x in args.extra_batches.split(",") if x]:
-            if qb == Q:
+    extra = [int(x) for x in args.extra_batches.split(",") if x and int(x) != Q]
+    head = run_workload(ctx, args.workload, [Q] + extra, args.steps, args.warmup, headline=True)
+    others = []
+    if args.others != "none":
+        spec = OTHER_WORKLOADS if args.others == "default" else tuple(
+            (s.split(":")[0], tuple(int(x) for x in s.split(":")[1:])) for s in args.others.split(",") if s)
+        for name, batches in spec:
+            if name == args.workload:
                 continue
-            pool = make_batches(qb, 2)
-            ms_b, _, km = run_device(pool, max(5, args.steps // 2), 3, profile=True)
-            steps_b = max(5, args.steps // 2)
-            bb, ff = algorithmic_work(n_shard, n_dense, 0 if bm25_mode else n_sparse, qb)
-            kk = statistics.mean(km) if km else None
-            extra.append({"batch": qb, "value": qb * steps_b / (ms_b * 1e-3), "ms_per_step": ms_b / steps_b,
-                          "kernel_ms": kk,
-                          "hbm_gbs": bb / (kk * 1e-3) / 1e9 if kk else None,
-                          "hbm_frac": bb / (kk * 1e-3) / 1e9 / peaks["hbm_gbs"] if kk else None,
-                          "tflops": ff / (kk * 1e-3) / 1e12 if kk else None})
-            del pool
+            try:
+                others.append(run_workload(ctx, name, list(batches), args.steps, args.warmup))
+            except Exception as e:  # noqa: BLE001  (a side workload must not take the headline down)
+                others.append({"workload": name, "error": f"{type(e).__name__}: {e}"[:300]})
 
     cpu_base = None
     if rank == 0 and world == 1 and args.cpu_budget_s > 0:
-        cpu_base, _ = cpu_reference_leg(n_total, n_dense, n_sparse, Q, args.seed, args.cpu_budget_s, 3, 1)
+        cpu_base = cpu_reference_leg(n_total, n_dense, n_sparse, Q, args.seed, 3, 1)
 
     if rank == 0:
+        main_rec = head["batches"][0]
+
+        def compact(rec):
+            r = rec.get("roofline") or {}
+            return {"batch": rec["batch"], "value": rec["value"], "ms_per_step": rec["ms_per_step"],
+                    "kernel": r.get("kernel"), "kernel_ms": r.get("kernel_ms"), "bound": r.get("bound"),
+                    "achieved": r.get("achieved"), "unit": r.get("unit"), "frac": r.get("frac"),
+                    "frac_of_burst_peak": r.get("frac_of_burst_peak"),
+                    "kernel_share_of_step": r.get("kernel_share_of_step"), "gpu_launches": rec["gpu_launches"]}
         line = {
-            "metric": METRIC, "value": Q * args.steps / (ms_total * 1e-3), "unit": "queries/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": main_rec["value"], "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_rec["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
-            "roofline": roof, "cpu_baseline": cpu_base,
-            "e2e": {"value": Q * args.steps / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "path": "mfar_search_host (C ABI, pinned host buffers)" if world == 1 else
-                            "pinned host -> device copies + sharded search + D2H of the merged top-k"},
-            "sparse_stage": sparse_stage, "gpu_launches": launches, "exchange": exchange_kind, "clocks": clocks, "other_batches": extra, "setup_s": setup_s,
-            "kernel_impl": args.kernel, "cuda_graph": bool(args.graph and world == 1),
+            "roofline": main_rec["roofline"], "cpu_baseline": cpu_base, "e2e": main_rec["e2e"],
+            "parity_check": head["parity_check"], "gpu_launches": main_rec["gpu_launches"],
+            "exchange": ctx.exchange_kind, "clocks": main_rec["clocks"],
+            "other_batches": [compact(r) for r in head["batches"][1:]],
+            "other_workloads": [
+                o if "error" in o else
+                {"workload": o["workload"], "n_docs": o["n_docs"], "n_dense": o["n_dense"], "n_sparse": o["n_sparse"],
+                 "shard_docs": o["shard_docs"], "parity_check": o["parity_check"],
+                 "batches": [compact(r) for r in o["batches"]]} for o in others],
+            "setup_s": head["setup_s"], "kernel_impl": args.kernel, "cuda_graph": head["cuda_graph"],
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

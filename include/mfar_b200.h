@@ -230,6 +230,13 @@ MFAR_API size_t mfar_exchange_buffer_bytes(int world, int q_cap, int k_cap);
 MFAR_API int mfar_topk_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
                              const uint64_t* peer_buffers_host, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
                              float* out_scores, int64_t* out_ids, void* stream);
+/* Same exchange with the call counter kept in DEVICE memory (int32, zero before the first call, owned by the caller):
+ * the call enqueues a one-thread kernel that increments it, then the exchange kernel that reads it - no host-side value
+ * is baked into the launch, so the whole sharded step (mixture weights, scoring, local merge, exchange) can be captured
+ * once in a CUDA graph and replayed.  Every rank must issue the same number of calls. */
+MFAR_API int mfar_topk_exchange_merge_dev_epoch(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
+                                       const uint64_t* peer_buffers_host, int q_cap, int k_cap, int32_t* epoch_dev,
+                                       uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* stream);
 
 /* Reference quirk, mfar/data/index.py:192-193: the running top-k starts as k entries of
  * (score 0.0, row 0).  Applies that to a finished [Q,k] result in place: entries scoring

@@ -420,10 +420,13 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 
 __global__ void __launch_bounds__(kMergeThreads)
 exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int k_in, PeerBufs peers, int rank, int world, int q_cap,
-                      int k_cap, int epoch, int k, uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
-                      int64_t* __restrict__ out_ids, int* __restrict__ err) {
+                      int k_cap, int epoch_arg, const int* __restrict__ epoch_dev, int k, uint64_t* __restrict__ out_keys,
+                      float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int* __restrict__ err) {
   __shared__ uint64_t buf[kMergeBuf];
   const int q = blockIdx.x, t = threadIdx.x;
+  // the call counter: a kernel argument, or - so that the launch can be replayed from a CUDA graph - a device word
+  // that bump_epoch_kernel (same stream, just before this kernel) increments
+  const int epoch = epoch_dev ? *epoch_dev : epoch_arg;
   const int parity = epoch & 1;
   const size_t flag_bytes = size_t(2) * world * q_cap * sizeof(int);
   const size_t slot = (size_t(parity) * world + rank) * q_cap + q;            // [parity][rank][q]
@@ -468,6 +471,8 @@ exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int k_in, PeerBuf
     if (out_ids) out_ids[int64_t(q) * k + j] = key ? int64_t(key_doc(key)) : int64_t(-1);
   }
 }
+
+__global__ void bump_epoch_kernel(int* epoch_dev) { *epoch_dev += 1; }
 
 // index.py:192-193 quirk: running top-k starts as (0.0, row 0) entries.
 __global__ void zero_init_kernel(float* scores, int64_t* ids, int n) {
@@ -604,16 +609,17 @@ int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, i
 }
 
 int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
-                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
-                          float* out_scores, int64_t* out_ids, cudaStream_t st) {
+                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, int* epoch_dev,
+                          uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   if (world < 1 || world > kMaxPeers || world * k_in > kMergeBuf || Q > q_cap || k_in > k_cap) return MFAR_ERR_SHAPE;
   PeerBufs pb{};
   for (int r = 0; r < world; ++r) pb.base[r] = peer_bases[r];
   // the error word lives at the very end of this rank's buffer
   int* err = reinterpret_cast<int*>(pb.base[rank] + size_t(2) * world * q_cap * sizeof(int) +
                                     size_t(2) * world * q_cap * k_cap * sizeof(uint64_t));
-  exchange_merge_kernel<<<Q, kMergeThreads, 0, st>>>(local_keys, k_in, pb, rank, world, q_cap, k_cap, epoch, k, out_keys,
-                                                     out_scores, out_ids, err);
+  if (epoch_dev) bump_epoch_kernel<<<1, 1, 0, st>>>(epoch_dev);
+  exchange_merge_kernel<<<Q, kMergeThreads, 0, st>>>(local_keys, k_in, pb, rank, world, q_cap, k_cap, epoch, epoch_dev, k,
+                                                     out_keys, out_scores, out_ids, err);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }

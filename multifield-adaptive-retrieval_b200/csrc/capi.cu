@@ -440,7 +440,21 @@ int mfar_topk_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k,
   if (int rc = check_arch()) return rc;
   return launch_exchange_merge(local_keys, Q, k_in, k, rank, world,
                                reinterpret_cast<const unsigned long long*>(peer_buffers_host), q_cap, k_cap, epoch,
-                               out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+                               nullptr, out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+}
+
+int mfar_topk_exchange_merge_dev_epoch(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
+                                       const uint64_t* peer_buffers_host, int q_cap, int k_cap, int32_t* epoch_dev,
+                                       uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* stream) {
+  if (!local_keys || !peer_buffers_host || !epoch_dev || Q <= 0 || k_in <= 0 || rank < 0 || rank >= world)
+    return MFAR_ERR_ARG;
+  if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
+  for (int r = 0; r < world; ++r)
+    if (!peer_buffers_host[r] || peer_buffers_host[r] % 16 != 0) return MFAR_ERR_ARG;
+  if (int rc = check_arch()) return rc;
+  return launch_exchange_merge(local_keys, Q, k_in, k, rank, world,
+                               reinterpret_cast<const unsigned long long*>(peer_buffers_host), q_cap, k_cap, 0,
+                               epoch_dev, out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
 }
 
 int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* stream) {

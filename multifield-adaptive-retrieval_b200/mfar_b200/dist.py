@@ -9,7 +9,7 @@ the same merge kernel - replacing the reference's ``{rank}.qres`` files + barrie
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -20,6 +20,23 @@ from . import _native as nv
 
 def shard_range(n_docs: int, rank: int, world: int) -> Tuple[int, int]:
     return n_docs * rank // world, n_docs * (rank + 1) // world
+
+
+def weighted_shard_ranges(n_docs: int, weights: Sequence[float], align: int = 128) -> List[Tuple[int, int]]:
+    """Contiguous doc-id ranges with sizes proportional to ``weights`` (one per rank, e.g. measured docs/s of each
+    GPU), boundaries rounded to ``align`` docs.  Every step of a sharded search ends with an exchange that waits for the
+    slowest rank, so on a node whose GPUs settle at different clocks under the power cap an equal split runs at the pace
+    of the slowest GPU; a speed-weighted split lets every rank finish together.  Equal weights reproduce
+    ``shard_range`` up to the rounding."""
+    w = [max(float(x), 1e-12) for x in weights]
+    total = sum(w)
+    cuts, acc = [0], 0.0
+    for x in w[:-1]:
+        acc += x
+        c = int(round(n_docs * acc / total / align)) * align
+        cuts.append(min(max(c, cuts[-1]), n_docs))
+    cuts.append(n_docs)
+    return [(cuts[i], cuts[i + 1]) for i in range(len(w))]
 
 
 # ---- host-side mirror of the device key packing (csrc/common.cuh) - used by tests and debugging
@@ -88,6 +105,10 @@ class PeerExchange:
             dist.barrier(group)                           # every rank's flags are zero before anyone pushes
         import ctypes
         self._ptr_arr = (ctypes.c_uint64 * self.world)(*self.ptrs)
+        # the call counter lives on the device and is incremented by a one-thread kernel in front of every exchange, so a
+        # merge call is identical from launch to launch and can be replayed from a CUDA graph
+        dev = peer_buffers[self.rank].device if peer_buffers is not None else self._bufs[0].device
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)
 
     @staticmethod
     def buffer_bytes(world: int, q_cap: int, k_cap: int = 128) -> int:
@@ -100,12 +121,12 @@ class PeerExchange:
         Q, k_in = keys.shape
         if Q > self.q_cap or k_in > self.k_cap:
             raise ValueError(f"exchange buffers sized for [{self.q_cap},{self.k_cap}], got [{Q},{k_in}]")
-        self.epoch += 1
+        self.epoch += 1                                   # bookkeeping only (calls issued or captured so far)
         scores = torch.empty((Q, k), dtype=torch.float32, device=keys.device)
         ids = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
-        nv.check(nv.lib().mfar_topk_exchange_merge(nv.ptr(keys.contiguous()), Q, k_in, k, self.rank, self.world,
-                                                   ctypes.addressof(self._ptr_arr), self.q_cap, self.k_cap, self.epoch,
-                                                   0, nv.ptr(scores), nv.ptr(ids), nv.stream()), "topk_exchange_merge")
+        nv.check(nv.lib().mfar_topk_exchange_merge_dev_epoch(
+            nv.ptr(keys.contiguous()), Q, k_in, k, self.rank, self.world, ctypes.addressof(self._ptr_arr), self.q_cap,
+            self.k_cap, nv.ptr(self.epoch_dev), 0, nv.ptr(scores), nv.ptr(ids), nv.stream()), "topk_exchange_merge")
         return scores, ids
 
 

@@ -585,14 +585,20 @@ class GraphedSearch:
     For small shards (PRIME-2k, Q=64: the kernels take ~60 us, the 4-5 launches with their Python/ctypes calls ~110 us)
     the step is launch-bound and the graph removes that; for corpus-sized shards it changes nothing.
 
-    Inputs are copied into static device buffers (``copy_`` accepts host or device tensors), outputs are the static
-    ``scores`` / ``ids`` tensors (valid until the next call).  BM25 token entries are padded to ``max_entries`` rows
+    Inputs are copied into static device buffers (``copy_`` accepts host or device tensors; a ``sparse_buffer`` given at
+    construction is adopted as the static sparse input and filled by the caller), outputs are the static ``scores`` /
+    ``ids`` tensors (valid until the next call).  BM25 token entries are padded to ``max_entries`` rows
     with (-1, 0, 0), which the plan kernel skips.  The graph holds the retriever's mask / weight tensors as they were at
     capture time: build a new GraphedSearch after ``mask_field``."""
 
     def __init__(self, retriever: "MultiFieldRetriever", batch: int, sparse: str = "none", max_entries: int = 0,
-                 top_k: Optional[int] = None, sparse_dtype=torch.float16, sparse_ld: Optional[int] = None):
+                 top_k: Optional[int] = None, sparse_dtype=torch.float16, sparse_ld: Optional[int] = None,
+                 sharded=None, sparse_buffer: Optional[torch.Tensor] = None):
+        """``sharded``: the ``mfar_b200.dist.ShardedRetriever`` wrapping ``retriever`` - the captured step then also holds
+        the cross-GPU exchange + merge (its call counter lives in device memory, so the replayed launch is identical on
+        every call); every rank must construct and call its GraphedSearch the same number of times."""
         r = self.r = retriever
+        self.sharded = sharded
         dev = r.device
         self.k = top_k or r.top_k
         self.Q = int(batch)
@@ -603,8 +609,11 @@ class GraphedSearch:
         self.q_emb = torch.zeros((self.Q, E), dtype=torch.float32, device=dev) if E else None
         self.sparse = self.entries = None
         if sparse == "dense":
-            ld = sparse_ld or _round_up(r.n_docs, 64)     # 32-byte aligned rows: gathered inside the scoring epilogue
-            self.sparse = torch.zeros((self.Q, r.n_sparse, ld), dtype=sparse_dtype, device=dev)
+            if sparse_buffer is not None:                 # adopt the caller's [Q,Fs,ld] tensor as the static input: a
+                self.sparse = sparse_buffer               # corpus-sized score tensor is not copied per replay
+            else:
+                ld = sparse_ld or _round_up(r.n_docs, 64)  # 32-byte aligned rows: gathered inside the scoring epilogue
+                self.sparse = torch.zeros((self.Q, r.n_sparse, ld), dtype=sparse_dtype, device=dev)
         elif sparse == "bm25":
             if r.bm25 is None or max_entries <= 0:
                 raise ValueError("sparse='bm25' needs a retriever with sparse_indices and max_entries > 0")
@@ -623,9 +632,11 @@ class GraphedSearch:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.scores, self.ids = self._run()
-        self.launches = r.last_launches + 1                # + mixture weights
+        self.launches = r.last_launches + 1 + (2 if sharded is not None else 0)   # + mixture weights (+ epoch bump, exchange)
 
     def _run(self):
+        if self.sharded is not None:
+            return self.sharded.search(self.q_vecs, self.q_emb, self.sparse, top_k=self.k, sparse_tokens=self.entries)
         return self.r.search(self.q_vecs, self.q_emb, self.sparse, top_k=self.k, sparse_tokens=self.entries,
                              batch=self.Q)
 
@@ -634,7 +645,7 @@ class GraphedSearch:
             self.q_vecs.copy_(q_vecs, non_blocking=True)
         if self.q_emb is not None:
             self.q_emb.copy_(q_emb if q_emb is not None else q_vecs, non_blocking=True)
-        if self.sparse is not None:
+        if self.sparse is not None and sparse is not None and sparse.data_ptr() != self.sparse.data_ptr():
             self.sparse[:, :, : sparse.shape[2]].copy_(sparse, non_blocking=True)
         if self.entries is not None:
             n = entries.shape[0]

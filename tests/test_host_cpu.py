@@ -287,3 +287,24 @@ def test_sweep_case_generators_stay_inside_the_kernels_envelope():
         t = F.draw_train_case(rng)
         assert t["E"] % 4 == 0 and t["E"] <= 1024
     assert set(F.MODES) == {"kernels", "api", "bm25", "train"}
+
+
+def test_weighted_shard_ranges_cover_the_corpus_and_follow_the_weights():
+    from mfar_b200.dist import shard_range, weighted_shard_ranges
+    n = 10_000_000
+    eq = weighted_shard_ranges(n, [1.0] * 8)
+    assert eq[0][0] == 0 and eq[-1][1] == n and all(a[1] == b[0] for a, b in zip(eq, eq[1:]))
+    assert all(abs((hi - lo) - n / 8) <= 128 for lo, hi in eq)
+    assert all(lo % 128 == 0 for lo, _ in eq)
+    assert all(abs(lo - shard_range(n, r, 8)[0]) <= 64 for r, (lo, _) in enumerate(eq))
+    w = [1.00, 0.96, 1.02, 0.99, 1.03, 0.97, 1.0, 1.01]
+    ws = weighted_shard_ranges(n, w)
+    assert ws[0][0] == 0 and ws[-1][1] == n and all(a[1] == b[0] for a, b in zip(ws, ws[1:]))
+    sizes = [hi - lo for lo, hi in ws]
+    for s_, w_ in zip(sizes, w):
+        assert abs(s_ - n * w_ / sum(w)) <= 256
+    # degenerate inputs: a tiny corpus, a zero weight
+    tiny = weighted_shard_ranges(100, [1, 1, 1, 1])
+    assert tiny[0][0] == 0 and tiny[-1][1] == 100 and all(lo <= hi for lo, hi in tiny)
+    z = weighted_shard_ranges(1000, [1.0, 0.0, 1.0], align=1)
+    assert z[1][1] - z[1][0] <= 1 and z[-1][1] == 1000
