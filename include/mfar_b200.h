@@ -321,8 +321,9 @@ MFAR_API int mfar_last_launch_count(void);
  * bench.py reports.  mfar_profile_enable(1) arms a ring of 256 CUDA event pairs recorded on the launch
  * stream around the scoring kernel of each subsequent mfar_score_topk call; mfar_profile_collect()
  * synchronises those events, writes their durations (ms) to a HOST array, returns how many, and
- * resets the ring.  Diagnostics only: the ring is process-global and not thread-safe (arm it from the one
- * thread that drives the GPU); it is off by default and the compute entry points never depend on it. */
+ * resets the ring.  Diagnostics only.  The ring is per host thread (thread-local state, events on the thread's current
+ * device): arm and collect it from the thread that issues the calls; other threads / devices are unaffected.  It is off
+ * by default and the compute entry points never depend on it. */
 MFAR_API int mfar_profile_enable(int on);
 MFAR_API int mfar_profile_collect(float* out_ms_host, int max_n);
 

@@ -597,11 +597,10 @@ int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, i
   int sc_cap = int(std::min<int64_t>(int64_t(L) * slots, 38 * 1024));
   sc_cap = (sc_cap + 3) & ~3;
   const size_t smem = size_t(sc_cap) * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MFAR_CUDA_OK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  MFAR_CUDA_OK(attr_once.run([&] {
+    return cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  }));
   merge_kernel<<<Q, kMergeThreads, smem, st>>>(keys, counts, thr, L, q_stride, slots, k, sc_cap, out_keys, out_scores,
                                               out_ids);
   MFAR_CUDA_OK(cudaGetLastError());

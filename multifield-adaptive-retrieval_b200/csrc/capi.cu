@@ -10,21 +10,25 @@ static thread_local int t_last_launches = 0;
 
 // Optional per-launch timing of the scoring kernel (bench.py's roofline): a ring of CUDA event pairs recorded
 // on the launch stream around the scoring kernel only.  Off by default; costs two event records per call.
+// The ring belongs to the calling host thread (thread_local): two threads driving two streams - or two devices - each
+// see only their own launches; events are created on the thread's current device when profiling is switched on.
 constexpr int kProfRing = 256;
-static bool g_prof_on = false;
-static cudaEvent_t g_prof_ev[kProfRing][2];
-static bool g_prof_init = false;
-static int g_prof_n = 0;
+static thread_local bool g_prof_on = false;
+static thread_local cudaEvent_t g_prof_ev[kProfRing][2];
+static thread_local int g_prof_dev = -1;     // device the events were created on (-1: none yet)
+static thread_local int g_prof_n = 0;
 
+// compute-capability check, cached per device (a process may drive several)
 static int check_arch() {
-  static int cached = -1;   // one process per GPU
-  if (cached >= 0) return cached;
+  constexpr int kMaxDev = 64;
+  static int cached[kMaxDev];                 // 0 = unknown, 1 = sm_100, 2 = other (benign race: idempotent writes)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return MFAR_ERR_CUDA;
+  if (dev >= 0 && dev < kMaxDev && cached[dev]) return cached[dev] == 1 ? MFAR_OK : MFAR_ERR_ARCH;
   int major = 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return MFAR_ERR_CUDA;
-  cached = (major == 10) ? MFAR_OK : MFAR_ERR_ARCH;
-  return cached;
+  if (dev >= 0 && dev < kMaxDev) cached[dev] = (major == 10) ? 1 : 2;
+  return major == 10 ? MFAR_OK : MFAR_ERR_ARCH;
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -87,7 +91,9 @@ const char* mfar_status_string(int status) {
   switch (status) {
     case MFAR_OK: return "ok";
     case MFAR_ERR_ARG: return "invalid argument (null / non-positive / misaligned)";
-    case MFAR_ERR_SHAPE: return "shape outside the supported envelope";
+    case MFAR_ERR_SHAPE:
+      return "shape outside the supported envelope (fields <= 64, k <= 128, doc_id_base + n_docs <= 2^32, dims the "
+             "selected kernel supports)";
     case MFAR_ERR_ARCH: return "device is not sm_100 (no fallback path exists)";
     case MFAR_ERR_WORKSPACE: return "workspace too small";
     case MFAR_ERR_CUDA: return "CUDA call failed";
@@ -659,10 +665,17 @@ int mfar_mixture_bwd(const float* x, const float* q_emb, const float* W, const f
 int mfar_last_launch_count(void) { return t_last_launches; }
 
 int mfar_profile_enable(int on) {
-  if (on && !g_prof_init) {
-    for (int i = 0; i < kProfRing; ++i)
-      for (int j = 0; j < 2; ++j) MFAR_CUDA_OK(cudaEventCreate(&g_prof_ev[i][j]));
-    g_prof_init = true;
+  if (on) {
+    int dev = 0;
+    MFAR_CUDA_OK(cudaGetDevice(&dev));
+    if (g_prof_dev != dev) {                    // first use on this thread, or the thread moved to another device
+      if (g_prof_dev >= 0)
+        for (int i = 0; i < kProfRing; ++i)
+          for (int j = 0; j < 2; ++j) cudaEventDestroy(g_prof_ev[i][j]);
+      for (int i = 0; i < kProfRing; ++i)
+        for (int j = 0; j < 2; ++j) MFAR_CUDA_OK(cudaEventCreate(&g_prof_ev[i][j]));
+      g_prof_dev = dev;
+    }
   }
   g_prof_on = on != 0;
   g_prof_n = 0;

@@ -28,6 +28,22 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
     }                                                                                        \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remembered per device so that a process
+// driving several GPUs raises the limit on each of them.  `done` is a static per call site / template instantiation.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  template <class Fn>
+  cudaError_t run(Fn&& fn) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = fn();
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+  }
+};
+
 // ---------------------------------------------------------------------------------------
 // (score, doc id) <-> order-preserving 64-bit key.
 //   high 32 bits: float score mapped so that unsigned order == float order

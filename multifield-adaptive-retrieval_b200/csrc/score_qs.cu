@@ -633,12 +633,10 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
                                      uint32_t(a.n_sparse), uint64_t(a.Q), kQsQ);
     if (rc) return rc;
   }
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    MFAR_CUDA_OK(cudaFuncSetAttribute(score_qs_kernel<CG, ES, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(smem_cap)));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;   // per template instantiation
+  MFAR_CUDA_OK(attr_once.run([&] {
+    return cudaFuncSetAttribute(score_qs_kernel<CG, ES, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap));
+  }));
   // lockstep counters of the query groups (producer warp) + shared per-query thresholds (epilogue)
   MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));
   cudaLaunchConfig_t cfg{};

@@ -434,11 +434,10 @@ static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   rc = make_tensor_map_2d(&map_b, a.q_vecs, uint64_t(a.Q), a.dim, QP, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (rc) return rc;
 
-  static bool attr_set = false;   // per template instantiation
-  if (!attr_set) {
-    MFAR_CUDA_OK(cudaFuncSetAttribute(score_tc_kernel<QP, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap)));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;   // per template instantiation
+  MFAR_CUDA_OK(attr_once.run([&] {
+    return cudaFuncSetAttribute(score_tc_kernel<QP, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap));
+  }));
   MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));   // shared thresholds
   dim3 grid(workers, q_tiles);
   score_tc_kernel<QP, SP><<<grid, SP ? kTcThreads + kStagerThreads : kTcThreads, smem, st>>>(map_a, map_b, p);

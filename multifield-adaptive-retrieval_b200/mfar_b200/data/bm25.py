@@ -32,7 +32,8 @@ _TOKEN_RE = re.compile(r"(?u)\b\w\w+\b")
 def tokenize(texts: Union[str, Sequence[str]], stopwords: Union[str, Sequence[str], None] = "en",
              stemmer: Optional[object] = None) -> List[List[str]]:
     """``bm25s.tokenize(texts, stopwords=..., stemmer=..., return_ids=False)`` (index.py:64,139): lower-case,
-    ``\\b\\w\\w+\\b`` tokens, stop words dropped, optional stemmer (a callable or an object with ``stemWords``)."""
+    ``\\b\\w\\w+\\b`` tokens, stop words dropped, optional stemmer (an object with ``stemWords`` or a callable that maps a
+    token list to a token list, as bm25s calls it)."""
     if isinstance(texts, str):
         texts = [texts]
     stop = set(STOPWORDS_EN if stopwords in ("en", "english", True) else (stopwords or ()))
@@ -40,7 +41,8 @@ def tokenize(texts: Union[str, Sequence[str]], stopwords: Union[str, Sequence[st
     for text in texts:
         toks = [t for t in _TOKEN_RE.findall(text.lower()) if t not in stop]
         if stemmer is not None:
-            toks = stemmer.stemWords(toks) if hasattr(stemmer, "stemWords") else [stemmer(t) for t in toks]
+            # bm25s' contract: a PyStemmer-like object, or a callable applied to the WHOLE token list
+            toks = list(stemmer.stemWords(toks)) if hasattr(stemmer, "stemWords") else list(stemmer(toks))
         out.append(toks)
     return out
 
@@ -288,11 +290,32 @@ class DeviceBM25:
             raise ValueError(f"k of {k} is larger than the number of available scores, which is {self.num_docs}")
         from ..modeling.retrieval import MultiFieldRetriever
         from ..modeling.weighting import LinearWeights
-        r = MultiFieldRetriever(None, LinearWeights(1, 1).to(self.device), top_k=k, n_docs=self.num_docs,
-                                device=self.device, sparse_indices=[self])
-        s, i = r.search(None, sparse_tokens=[query_tokens], top_k=k)
-        self.last_launches = r.last_launches
-        return i.cpu().numpy(), s.cpu().numpy()
+        if k <= nv.MAX_K:
+            r = MultiFieldRetriever(None, LinearWeights(1, 1).to(self.device), top_k=k, n_docs=self.num_docs,
+                                    device=self.device, sparse_indices=[self])
+            s, i = r.search(None, sparse_tokens=[query_tokens], top_k=k)
+            self.last_launches = r.last_launches
+            return i.cpu().numpy(), s.cpu().numpy()
+        # k above the streaming top-k's 128 (the reference's precompute asks for 150, precompute_bm25s_scores.py:60):
+        # score once, then peel the ranking off in passes of <= 128 - each pass is the same streaming top-k kernel over
+        # the score rows, the docs already taken are sunk to -inf in between.  Passes come out in rank order.
+        Q, n = len(query_tokens), self.num_docs
+        ld = (n + 63) // 64 * 64
+        rows = torch.full((Q, 1, ld), float("-inf"), dtype=torch.float32, device=self.device)
+        rows[:, 0, :n] = self.get_scores_batch(query_tokens)
+        r = MultiFieldRetriever(None, LinearWeights(1, 1).to(self.device), n_sparse=1, top_k=nv.MAX_K, n_docs=n,
+                                device=self.device)
+        out_s, out_i, left, launches = [], [], int(k), 0
+        while left > 0:
+            kk = min(left, nv.MAX_K)
+            s, i = r.search(None, sparse=rows, top_k=kk, batch=Q)
+            launches += r.last_launches
+            out_s.append(s)
+            out_i.append(i)
+            rows[:, 0, :].scatter_(1, i, float("-inf"))
+            left -= kk
+        self.last_launches = launches
+        return torch.cat(out_i, dim=1).cpu().numpy(), torch.cat(out_s, dim=1).cpu().numpy()
 
 
 class BM25FieldSet:

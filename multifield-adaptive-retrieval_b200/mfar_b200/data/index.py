@@ -90,7 +90,15 @@ class DenseFlatIndex(Index[str, str]):
 
     def retrieve_batch(self, queries, top_k: int) -> List[List[Tuple[str, float]]]:
         r = self._ensure()
-        s, i = r.per_field_topk(self._encode(queries), None, top_k, zero_init=True)
+        k_eff = min(int(top_k), r.n_docs)
+        s, i = r.per_field_topk(self._encode(queries), None, k_eff, zero_init=True)
+        if k_eff < top_k:
+            # more hits requested than the field holds: the reference's running top-k starts as top_k entries of
+            # (0.0, row 0) (index.py:192-193) and those that no real score displaces stay - after the zero-init rule
+            # every kept score is >= 0, so they are exactly the tail
+            pad = int(top_k) - k_eff
+            s = torch.nn.functional.pad(s, (0, pad), value=0.0)
+            i = torch.nn.functional.pad(i, (0, pad), value=0)
         rows, vals = i[0].cpu().tolist(), s[0].cpu().tolist()
         return [list(zip([self.numeric_ids_to_key[j] for j in rows[q]], vals[q])) for q in range(len(rows))]
 
@@ -198,8 +206,10 @@ class BM25sSparseIndex(Index[str, str]):
 
     def score_batch_with_cache(self, query_ids: List[int], keys: Sequence[str], sparse_scores: Dict) -> torch.Tensor:
         """index.py:120-125: lookup in precomputed ``{qid: {doc_id: score}}`` dicts, missing -> 0."""
-        all_doc_scores = [sparse_scores.get(qid, {}) for qid in query_ids]
         doc_ids = [self.key_to_id[key] for key in keys]
+        if hasattr(sparse_scores, "score_matrix"):                   # FieldSparseScores: sorted arrays, vectorised
+            return torch.from_numpy(sparse_scores.score_matrix(query_ids, doc_ids))
+        all_doc_scores = [sparse_scores.get(qid, {}) for qid in query_ids]
         return torch.tensor([[s.get(d, 0) for d in doc_ids] for s in all_doc_scores])
 
     @classmethod

@@ -235,17 +235,25 @@ class MultiFieldRetriever:
             return sparse_tokens.contiguous()
         return self.bm25.entries(sparse_tokens)
 
-    def _sparse_from_tokens(self, sparse, sparse_tokens, q_bf16) -> Optional[torch.Tensor]:
+    @staticmethod
+    def _batch_size(q_bf16, sparse, sparse_tokens, batch: Optional[int]) -> int:
+        """Number of queries of a call.  A prebuilt int32 [n,3] entry tensor does not carry it (trailing queries may
+        have no tokens at all): a sparse-only retriever fed with one needs ``batch=``."""
+        if q_bf16 is not None:
+            return int(q_bf16.shape[0])
+        if sparse is not None:
+            return int(sparse.shape[0])
+        if batch is not None:
+            return int(batch)
+        if sparse_tokens is not None and not torch.is_tensor(sparse_tokens):
+            return len(sparse_tokens[0])
+        raise ValueError("cannot infer the batch size: pass batch= (sparse-only retriever with an entry tensor)")
+
+    def _sparse_from_tokens(self, sparse, sparse_tokens, q_bf16, batch: Optional[int] = None) -> Optional[torch.Tensor]:
         """Per-field score tensor [Q,F_s,ld] from query tokens when the sparse fields are BM25 indices."""
         if sparse_tokens is None:
             return sparse
-        if q_bf16 is not None:
-            Q = q_bf16.shape[0]
-        elif torch.is_tensor(sparse_tokens):
-            Q = int(sparse_tokens[:, 0].max().item()) + 1 if sparse_tokens.numel() else 1
-        else:
-            Q = len(sparse_tokens[0])
-        return self.bm25_field_scores(sparse_tokens, Q)
+        return self.bm25_field_scores(sparse_tokens, self._batch_size(q_bf16, None, sparse_tokens, batch))
 
     def bm25_field_scores(self, sparse_tokens, Q: int) -> torch.Tensor:
         """fp32 [Q, F_s, ld>=N]: what ``get_scores`` returns for every (query, sparse field), on the device."""
@@ -277,19 +285,11 @@ class MultiFieldRetriever:
         Returns (scores [Q,k] fp32, ids [Q,k] int64) sorted by (score desc, id asc); with
         return_keys also the packed uint64 keys (as int64) used for cross-shard merging."""
         k = top_k or self.top_k
-        if self.corpus is not None:
-            q_bf16 = self.corpus.prepare_queries(q_vecs)
-            Q = q_bf16.shape[0]
-        elif sparse is not None:
-            q_bf16, Q = None, sparse.shape[0]
-        elif batch is not None:
-            q_bf16, Q = None, int(batch)
-        elif sparse_tokens is not None and not torch.is_tensor(sparse_tokens):
-            q_bf16, Q = None, len(sparse_tokens[0])
-        elif q_emb is not None:
-            q_bf16, Q = None, int(q_emb.shape[0])
-        else:
-            raise ValueError("cannot infer the batch size: pass batch= (sparse-only retriever with an entry tensor)")
+        q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
+        if q_bf16 is None and sparse is None and batch is None and q_emb is not None and (
+                sparse_tokens is None or torch.is_tensor(sparse_tokens)):
+            batch = int(q_emb.shape[0])
+        Q = self._batch_size(q_bf16, sparse, sparse_tokens, batch)
         if self.mixture.query_cond:
             qe = q_emb if q_emb is not None else (q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs))
             qe = qe.to(self.device).float()
@@ -344,7 +344,8 @@ class MultiFieldRetriever:
     @torch.no_grad()
     def search_mask_sweep(self, q_vecs, masked_sets: Sequence[Sequence[int]], q_emb: Optional[torch.Tensor] = None,
                           sparse: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
-                          max_rows: int = 1024, sparse_tokens=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                          max_rows: int = 1024, sparse_tokens=None, batch: Optional[int] = None
+                          ) -> Tuple[torch.Tensor, torch.Tensor]:
         """All M maskings of ``mask_field`` evaluated as extra weight rows of ONE fused pass per chunk: the mask only
         multiplies the softmax weights (contrastive.py:686, no renormalisation), so masking m of query q is the
         pseudo-query (q, w[q] * mask_m).  Returns (scores [M,Q,k], ids [M,Q,k]).  Rows are processed in chunks of
@@ -353,12 +354,7 @@ class MultiFieldRetriever:
         k = top_k or self.top_k
         q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
         ent = self._bm25_entries(sparse_tokens) if sparse_tokens is not None else None
-        if q_bf16 is not None:
-            Q = q_bf16.shape[0]
-        elif sparse is not None:
-            Q = sparse.shape[0]
-        else:
-            Q = len(sparse_tokens[0])
+        Q = self._batch_size(q_bf16, sparse, sparse_tokens, batch)
         if self.mixture.query_cond:
             qe = q_emb if q_emb is not None else (q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs))
             qe = qe.to(self.device).float()
@@ -481,14 +477,15 @@ class MultiFieldRetriever:
     # ------------------------------------------------------------------ per-field top-k (index.py:181-222)
     @torch.no_grad()
     def per_field_topk(self, q_vecs, sparse: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
-                       zero_init: bool = True, sparse_tokens=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       zero_init: bool = True, sparse_tokens=None, batch: Optional[int] = None
+                       ) -> Tuple[torch.Tensor, torch.Tensor]:
         """What ``index.retrieve_batch(queries, top_k)`` returns for every field, in field order:
         (scores [F,Q,k], rows [F,Q,k]).  Dense fields reproduce the reference's (0.0, row 0) running-top-k
         initialisation (index.py:192-193) when zero_init is set."""
         k = top_k or self.top_k
         q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
-        sparse = self._sparse_from_tokens(sparse, sparse_tokens, q_bf16)
-        Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
+        sparse = self._sparse_from_tokens(sparse, sparse_tokens, q_bf16, batch)
+        Q = self._batch_size(q_bf16, sparse, None, batch)
         sp, code = self._check_sparse(sparse, Q)
         ones = torch.ones((Q, 1), dtype=torch.float32, device=self.device)
         all_s, all_i = [], []
@@ -509,11 +506,11 @@ class MultiFieldRetriever:
     # ------------------------------------------------------------------ candidate re-scoring (index.py:227-232)
     @torch.no_grad()
     def score_candidates(self, q_vecs, rows: torch.Tensor, sparse: Optional[torch.Tensor] = None,
-                         sparse_tokens=None) -> torch.Tensor:
+                         sparse_tokens=None, batch: Optional[int] = None) -> torch.Tensor:
         """Per-field scores of the given local rows: [F, Q, C] (rows < 0 -> 0, index.py:112-117)."""
         q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
-        sparse = self._sparse_from_tokens(sparse, sparse_tokens, q_bf16)
-        Q = q_bf16.shape[0] if q_bf16 is not None else sparse.shape[0]
+        sparse = self._sparse_from_tokens(sparse, sparse_tokens, q_bf16, batch)
+        Q = self._batch_size(q_bf16, sparse, None, batch)
         rows = rows.to(self.device, dtype=torch.int64).contiguous()
         C = rows.numel()
         out = torch.zeros((self.num_fields, Q, C), dtype=torch.float32, device=self.device)

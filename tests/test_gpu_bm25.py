@@ -83,10 +83,39 @@ def test_get_scores_and_retrieve_match_oracle():
     rows, vals = ix.retrieve(queries, k=100)
     all_s = np.stack([B.get_scores(oidx, t) for t in queries])
     assert_topk_parity(vals, rows, all_s, 100, rtol=2e-5)
+    # k above the streaming top-k's 128: the reference's precompute asks for the top 150 (precompute_bm25s_scores.py:60)
+    for k_big in (150, 300):
+        rows, vals = ix.retrieve(queries, k=k_big)
+        assert rows.shape == (17, k_big)
+        # most docs score exactly 0 for a query, so the tail of a deep ranking is one big tie: compare the scores rank by
+        # rank and the ids wherever the score is not tied
+        for q in range(17):
+            order = np.lexsort((np.arange(n_docs), -all_s[q].astype(np.float64)))[:k_big]
+            np.testing.assert_allclose(vals[q], all_s[q][order], rtol=2e-5, atol=1e-6)
+            assert len(set(rows[q].tolist())) == k_big
+            np.testing.assert_allclose(all_s[q][rows[q]], vals[q], rtol=2e-5, atol=1e-6)
     with pytest.raises(ValueError):
         ix.retrieve(queries, k=n_docs + 1)
     with pytest.raises(ValueError):
         ix.get_scores("not a list")
+
+
+def test_candidate_docs_with_the_reference_default_top_k_150():
+    """precompute_bm25s_scores.py:73-82 through the BM25sSparseIndex API with its default top_k=150 (> MFAR_MAX_K)."""
+    from mfar_b200.commands import precompute_bm25s_scores as C
+    from mfar_b200.data.index import BM25sSparseIndex
+    DeviceBM25 = _mods()[0]
+    rng = np.random.RandomState(3)
+    words = [f"w{i}" for i in range(300)]
+    docs = [" ".join(rng.choice(words, size=rng.randint(3, 20))) for _ in range(2000)]
+    from mfar_b200.data.bm25 import tokenize
+    ix = DeviceBM25(device=DEV).index(tokenize(docs))
+    index = BM25sSparseIndex([str(i) for i in range(len(docs))], ix, stemmer=None)
+    queries = [" ".join(rng.choice(words, size=6)) for _ in range(9)]
+    cand = C.candidate_docs(index, queries, {5, 7}, batch_size=4)
+    assert {5, 7} <= cand and len(cand) >= 150
+    hits = index.retrieve_batch(queries[:2], top_k=150)
+    assert len(hits) == 2 and len(hits[0]) == 150 and all(hits[0][j][1] >= hits[0][j + 1][1] for j in range(149))
 
 
 def test_many_entries_and_long_postings_cross_chunk_boundaries():

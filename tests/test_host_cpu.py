@@ -100,6 +100,11 @@ def test_memory_map_dict_is_headerless_fp32(tmp_path):
     assert len(m) == 7 and "d2" in m and "zz" not in m and list(m) == keys
     with pytest.raises(NotImplementedError):
         del m["d0"]
+    with pytest.raises(KeyError):
+        m["zz"]
+    assert m.rows_of(["d5", "d0"]).tolist() == [5, 0]
+    blocks = list(m.iter_row_blocks(3))
+    assert [lo for lo, _ in blocks] == [0, 3, 6] and blocks[1][1].shape == (3, 16) and blocks[1][1].flags["C_CONTIGUOUS"]
 
 
 def test_read_and_create_indices_wiring(tmp_path, monkeypatch):
@@ -308,3 +313,32 @@ def test_weighted_shard_ranges_cover_the_corpus_and_follow_the_weights():
     assert tiny[0][0] == 0 and tiny[-1][1] == 100 and all(lo <= hi for lo, hi in tiny)
     z = weighted_shard_ranges(1000, [1.0, 0.0, 1.0], align=1)
     assert z[1][1] - z[1][0] <= 1 and z[-1][1] == 1000
+
+
+def test_sparse_score_store_matches_the_reference_loader_golden(tmp_path):
+    """tests/golden/sparse_scores.npz was produced by the reference's own ``read_sparse_scores`` +
+    ``score_batch_with_cache`` (oracle/make_golden_sparse_scores.py): same [Q,C] matrices (missing -> 0, the later of
+    duplicate pairs wins), same ``qid in by_field`` answers, through the store and through ``BM25sSparseIndex``."""
+    import json as _json
+    from mfar_b200.data.index import BM25sSparseIndex
+    from mfar_b200.data.typedef import Field, FieldType
+    from mfar_b200.modeling.util import read_sparse_scores
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "sparse_scores.npz"))
+    meta = _json.loads(str(z["meta"]))
+    finfo = {"a_dense": Field("a_dense", "a", FieldType.DENSE), "a_sparse": Field("a_sparse", "a", FieldType.SPARSE),
+             "b_sparse": Field("b_sparse", "b", FieldType.SPARSE)}
+    for fk in ("a_sparse", "b_sparse"):
+        np.save(tmp_path / f"{fk}_keys_bm25.npy", z[f"{fk}_keys"])
+        np.save(tmp_path / f"{fk}_vals_bm25.npy", z[f"{fk}_vals"])
+    store = read_sparse_scores(str(tmp_path), finfo)
+    assert store.keys() == ["a_sparse", "b_sparse"] and len(store.values()) == 2 and bool(store)
+    keys_all = [str(i) for i in range(meta["n_docs"])]
+    index = BM25sSparseIndex(keys_all, index=None, stemmer=None)
+    for fk in store.keys():
+        by_field = store[fk]
+        assert [qid in by_field for qid in meta["query_ids"]] == z[f"{fk}_has_qid"].tolist()
+        got = index.score_batch_with_cache(meta["query_ids"], meta["cand"], by_field)
+        assert got.dtype == torch.float32 and np.array_equal(got.numpy(), z[f"{fk}_cached"])
+        # dict-style access agrees as well
+        row = by_field.get(meta["query_ids"][0], {})
+        assert all(np.float32(row.get(int(c), 0)) == z[f"{fk}_cached"][0, j] for j, c in enumerate(meta["cand"]))
