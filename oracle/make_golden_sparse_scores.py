@@ -4,7 +4,7 @@
 ``sentence_transformers.models`` stub for the import line mfar/modeling/util.py:14).
 
 Run in the build container only:   python oracle/make_golden_sparse_scores.py
-Writes tests/golden/sparse_scores.npz: the key / value files of two sparse fields (incl. duplicate pairs, for which
+Writes tests/golden/loader/sparse_scores.npz: the key / value files of two sparse fields (incl. duplicate pairs, for which
 the reference's dict keeps the LAST value) and the [Q, C] matrices the reference's cached scorer returns for them.
 
 Note (not mirrored): ``_create_sparse_index_from_npy`` chunks its input with start indices 0, 1, 2, ... instead of
@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_import  # noqa: E402
 
-GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden", "sparse_scores.npz")
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden", "loader", "sparse_scores.npz")
 
 
 def main():

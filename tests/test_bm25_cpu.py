@@ -101,7 +101,13 @@ def test_tokenizer_defaults():
     text = "The QUICK brown-fox is at a U.S. lab; it was not 3D, x y zz"
     assert tokenize(text)[0] == B.tokenize(text) == ["quick", "brown", "fox", "lab", "3d", "zz"]
     assert tokenize([text, ""], stopwords=None)[1] == []
-    assert tokenize("running runs", stemmer=lambda t: t[:3])[0] == ["run", "run"]
+    # bm25s calls a callable stemmer with the WHOLE token list; a PyStemmer-like object through .stemWords
+    assert tokenize("running runs", stemmer=lambda toks: [t[:3] for t in toks])[0] == ["run", "run"]
+
+    class Stem:
+        def stemWords(self, toks):
+            return [t.rstrip("s") for t in toks]
+    assert tokenize("runs cats", stemmer=Stem())[0] == ["run", "cat"]
 
 
 def test_token_entries_layout_and_vocabulary_lookup():

@@ -316,14 +316,14 @@ def test_weighted_shard_ranges_cover_the_corpus_and_follow_the_weights():
 
 
 def test_sparse_score_store_matches_the_reference_loader_golden(tmp_path):
-    """tests/golden/sparse_scores.npz was produced by the reference's own ``read_sparse_scores`` +
+    """tests/golden/loader/sparse_scores.npz was produced by the reference's own ``read_sparse_scores`` +
     ``score_batch_with_cache`` (oracle/make_golden_sparse_scores.py): same [Q,C] matrices (missing -> 0, the later of
     duplicate pairs wins), same ``qid in by_field`` answers, through the store and through ``BM25sSparseIndex``."""
     import json as _json
     from mfar_b200.data.index import BM25sSparseIndex
     from mfar_b200.data.typedef import Field, FieldType
     from mfar_b200.modeling.util import read_sparse_scores
-    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "sparse_scores.npz"))
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "loader", "sparse_scores.npz"))
     meta = _json.loads(str(z["meta"]))
     finfo = {"a_dense": Field("a_dense", "a", FieldType.DENSE), "a_sparse": Field("a_sparse", "a", FieldType.SPARSE),
              "b_sparse": Field("b_sparse", "b", FieldType.SPARSE)}
