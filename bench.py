@@ -555,6 +555,32 @@ class Workload:
             res.update({"ok": False, "error": str(e)[:300]})
         return res
 
+    # ------------------------------------------------------------------ the reference-faithful mode
+    def time_union_rescore(self, Q, steps, warmup):
+        """trec_eval_step as the reference runs it - per-field top-100, union, rescore, mixture, top-100 - on the device:
+        one streaming top-k pass per field + ONE union/rescore kernel for the batch (mfar_union_rescore).  Also reports
+        how much of the exhaustive top-100 the candidate-union pipeline recovers (it is an approximation of it)."""
+        pool = self.make_batches(Q, 2)
+        run = lambda b: self.retr.union_rescore_batch(b[0], b[1], b[2], TOPK)      # noqa: E731
+        for i in range(warmup):
+            run(pool[i % len(pool)])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            vals, rows, usize = run(pool[i % len(pool)])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = self.retr.last_launches
+        b = pool[(steps - 1) % len(pool)]
+        _, ids = self.retr.search(b[0], b[1], b[2])
+        overlap = [(len(set(rows[i].tolist()) & set((ids[i] - self.lo).tolist())) / TOPK) for i in range(min(Q, 16))]
+        return {"mode": "union_rescore (reference-faithful trec_eval_step on the device)", "batch": Q,
+                "value": Q * steps / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches_per_step": launches,
+                "mean_union_size": float(usize.float().mean().item()),
+                "overlap_with_exhaustive_top100": sum(overlap) / len(overlap)}
+
     def release(self):
         self.graphs.clear()
         self.retr = self.sharded = self.pc = self.bm25_fields = None
@@ -591,6 +617,11 @@ def run_workload(ctx: Ctx, name, batches, steps, warmup, headline=False):
         del pool
         gc.collect()
         torch.cuda.empty_cache()
+    if ctx.world == 1 and not wl.bm25_mode and name in ("prime_full", "amazon_full", "mag_full"):
+        try:
+            out["union_rescore"] = wl.time_union_rescore(64, max(5, steps // 2), 3)
+        except Exception as e:  # noqa: BLE001
+            out["union_rescore"] = {"error": f"{type(e).__name__}: {e}"[:200]}
     wl.release()
     return out
 
@@ -709,7 +740,8 @@ def main():
                 o if "error" in o else
                 {"workload": o["workload"], "n_docs": o["n_docs"], "n_dense": o["n_dense"], "n_sparse": o["n_sparse"],
                  "shard_docs": o["shard_docs"], "parity_check": o["parity_check"],
-                 "batches": [compact(r) for r in o["batches"]]} for o in others],
+                 "batches": [compact(r) for r in o["batches"]], "union_rescore": o.get("union_rescore")}
+                for o in others],
             "setup_s": head["setup_s"], "kernel_impl": args.kernel, "cuda_graph": head["cuda_graph"],
         }
         sys.stdout.flush()

@@ -238,6 +238,21 @@ MFAR_API int mfar_topk_exchange_merge_dev_epoch(const uint64_t* local_keys, int 
                                        const uint64_t* peer_buffers_host, int q_cap, int k_cap, int32_t* epoch_dev,
                                        uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* stream);
 
+/* The candidate stage of trec_eval_step (mfar/modeling/contrastive.py:676-696) for a whole batch in one launch: per
+ * query the union of the per-field hit lists (678-679), the re-scoring of that union under every field (681-683,
+ * DenseFlatIndex.score_batch / BM25sSparseIndex.score_batch), mask + mixture (685-694, folded into w) and the final
+ * top-k (696).
+ *   cand_rows : int64 [n_lists, Q, k_in] LOCAL doc rows, one list per field index as retrieve_batch returned them
+ *               (rows < 0 or >= n_docs are ignored); n_lists * k_in <= 8192;
+ *   w         : fp32 [Q, n_dense + n_sparse] = softmax(q@W) * mask (mfar_mixture_weights);
+ *   sparse    : [Q, n_sparse, sparse_ld] f16/f32 stored per-field scores of this shard's docs (or NULL);
+ *   out_scores fp32 [Q,k], out_rows int64 [Q,k] (local rows; score desc, row asc), out_union_size int32 [Q] = size of
+ *   each query's union - where it is below k the reference's torch.topk raises, and the tail is (-inf, -1) here. */
+MFAR_API int mfar_union_rescore(const void* corpus, int64_t n_docs, int corpus_fields, int n_dense, int dim,
+                       const void* q_vecs, int Q, const float* w, const void* sparse, int n_sparse, int sparse_dtype,
+                       int64_t sparse_ld, const int64_t* cand_rows, int n_lists, int k_in, int k, float* out_scores,
+                       int64_t* out_rows, int32_t* out_union_size, void* stream);
+
 /* Reference quirk, mfar/data/index.py:192-193: the running top-k starts as k entries of
  * (score 0.0, row 0).  Applies that to a finished [Q,k] result in place: entries scoring
  * below 0.0 are replaced by (0.0, 0) and the list re-sorted. */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("MFAR_OUT") or os.path.join(HERE, "mfar_b200", "libmfar_b200.so")   # MFAR_OUT: instrumented builds
 BUILD_DIR = os.path.join(HERE, "build" + ("_" + os.path.basename(OUT).replace(".", "_") if os.environ.get("MFAR_OUT") else ""))
-SOURCES = ["capi.cu", "aux_kernels.cu", "score_simt.cu", "score_tc.cu", "score_qs.cu", "bm25.cu", "train.cu", "topk_rows.cu", "sparse_coo.cu"]
+SOURCES = ["capi.cu", "aux_kernels.cu", "score_simt.cu", "score_tc.cu", "score_qs.cu", "bm25.cu", "train.cu", "topk_rows.cu", "sparse_coo.cu", "union_rescore.cu"]
 HEADERS = ["common.cuh", "kernels.h", "tc_ptx.cuh", os.path.join("..", "..", "include", "mfar_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

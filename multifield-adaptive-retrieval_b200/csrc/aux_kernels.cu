@@ -474,6 +474,19 @@ exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int k_in, PeerBuf
 
 __global__ void bump_epoch_kernel(int* epoch_dev) { *epoch_dev += 1; }
 
+__global__ void seed_gthr_kernel(unsigned long long* gthr, const unsigned long long* seed, int Q) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) gthr[q] = seed[q];
+}
+// key > (kth - 1)  <=>  key >= kth: the k-th best doc of the prefix itself must still be admitted by the main pass
+__global__ void seed_from_keys_kernel(const uint64_t* keys, int Q, int k, unsigned long long* seed) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) {
+    const uint64_t kth = keys[int64_t(q) * k + (k - 1)];
+    seed[q] = kth ? kth - 1ull : 0ull;
+  }
+}
+
 // index.py:192-193 quirk: running top-k starts as (0.0, row 0) entries.
 __global__ void zero_init_kernel(float* scores, int64_t* ids, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -619,6 +632,18 @@ int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, in
   if (epoch_dev) bump_epoch_kernel<<<1, 1, 0, st>>>(epoch_dev);
   exchange_merge_kernel<<<Q, kMergeThreads, 0, st>>>(local_keys, k_in, pb, rank, world, q_cap, k_cap, epoch, epoch_dev, k,
                                                      out_keys, out_scores, out_ids, err);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_seed_gthr(unsigned long long* gthr, const unsigned long long* seed, int Q, cudaStream_t st) {
+  seed_gthr_kernel<<<(Q + 255) / 256, 256, 0, st>>>(gthr, seed, Q);
+  MFAR_CUDA_OK(cudaGetLastError());
+  return MFAR_OK;
+}
+
+int launch_seed_from_keys(const uint64_t* keys, int Q, int k, unsigned long long* seed, cudaStream_t st) {
+  seed_from_keys_kernel<<<(Q + 255) / 256, 256, 0, st>>>(keys, Q, k, seed);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }

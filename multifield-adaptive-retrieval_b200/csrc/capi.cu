@@ -32,6 +32,7 @@ static int check_arch() {
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static size_t seed_scratch_bytes(int Q, int k) { return align_up(size_t(Q) * k * 8, 256) + align_up(size_t(Q) * 8, 256); }
 
 struct Geometry {
   int impl;       // resolved: MFAR_IMPL_SIMT, MFAR_IMPL_TCGEN05 or MFAR_IMPL_TCGEN05_QS
@@ -175,6 +176,7 @@ size_t mfar_score_topk_workspace_bytes(int Q, int k, int64_t n_docs, int n_spars
   }
   size_t total = align_up(best, 256);
   if (n_sparse > 0) total += align_up(size_t(Q) * size_t(align_up(size_t(n_docs), kTileDocs)) * 4, 256);
+  total += seed_scratch_bytes(Q, MFAR_MAX_K);         // threshold-seeding prefix pass
   return total;
 }
 
@@ -244,7 +246,10 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
                            sparse_rows_fusable(sp.dense, sp.dense_dtype, sp.dense_ld);
   const size_t ws_base = (n_sparse > 0 && !fuse_sparse) ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
   const size_t ws_plan = (n_sparse > 0 && sp.kind == 3) ? bm25_plan_bytes(sp.n_entries) : 0;
+  // prefix keys [Q,k] + seed thresholds [Q] of the threshold-seeding pass (used when the caller's workspace has room)
+  size_t ws_seed = seed_scratch_bytes(Q, k);
   if (workspace_bytes < ws_topk + ws_base + ws_plan) return MFAR_ERR_WORKSPACE;
+  if (workspace_bytes < ws_topk + ws_base + ws_plan + ws_seed) ws_seed = 0;
   if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MFAR_ERR_ARG;
 
   if (fuse_sparse) {
@@ -280,6 +285,36 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
     a.base_ld = base_ld;
   }
   int rc;
+  // Threshold seeding (tensor-core kernels, shards of >= 16 tiles per CTA): the same kernel first scores a PREFIX of one
+  // tile per CTA, the merge ranks it, and the k-th best key of the prefix (a valid lower bound of the shard's k-th key)
+  // becomes every query's initial admission threshold.  Without it every candidate list fills unfiltered and is
+  // compacted twice before the shared thresholds bite - 64 of the ~70 compactions per epilogue warp on a 700k-doc
+  // shard, ~10 % of that kernel plus the tensor-pipe stalls behind them; the prefix costs ~0.1 ms.
+  // Not for small batches: below ~32 queries there are few lists to compact and the prefix's fixed ~0.1 ms shows
+  // (measured: MAG-shaped Q=64 step 1.04 -> 0.93 ms, Q=512 2.82 -> 2.74 ms, 1.25M-doc shard Q=512 6.92 -> 6.60 ms,
+  // single_ Q=128 3.21 -> 2.73 ms; Q=1 0.81 -> 0.87 ms without this rule).
+  const bool seed = n_dense > 0 && (g.impl == MFAR_IMPL_TCGEN05 || g.impl == MFAR_IMPL_TCGEN05_QS) && Q >= 32 &&
+                    a.n_tiles >= 16 * g.workers && ws_seed > 0;
+  if (seed) {
+    char* sb = static_cast<char*>(workspace) + ws_topk + ws_base + ws_plan;
+    uint64_t* pref_keys = reinterpret_cast<uint64_t*>(sb);
+    unsigned long long* seed_thr = reinterpret_cast<unsigned long long*>(sb + align_up(size_t(Q) * k * 8, 256));
+    ScoreArgs ap = a;
+    ap.n_tiles = g.workers;
+    ap.n_docs = int64_t(g.workers) * kTileDocs;
+    ap.gthr_seed = nullptr;
+    const Geometry gp = resolve_geometry(ap, g.impl);
+    if (g.impl == MFAR_IMPL_TCGEN05_QS) rc = launch_score_qs(ap, workspace, gp.workers, gp.q_tiles, gp.cg, st);
+    else rc = launch_score_tc(ap, workspace, gp.workers, gp.q_tiles, gp.q_pad, st);
+    if (rc) return rc;
+    TopkWorkspace wp = carve_workspace(workspace, gp.lists, gp.q_pad_total);
+    rc = launch_merge(wp.cand_keys, wp.cand_cnt, wp.cand_thr, gp.lists, gp.q_pad_total, kCandCap, Q, k, pref_keys, nullptr,
+                      nullptr, st);
+    if (rc) return rc;
+    if ((rc = launch_seed_from_keys(pref_keys, Q, k, seed_thr, st))) return rc;
+    a.gthr_seed = seed_thr;
+    t_last_launches += 4;                             // prefix scoring + merge + seed, and the copy into the main pass
+  }
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][0], st));
   if (g.impl == kImplRows)
@@ -476,6 +511,28 @@ int mfar_score_candidates(const void* corpus, int64_t n_docs, int corpus_fields,
   if (int rc = check_arch()) return rc;
   return launch_score_candidates(corpus, n_docs, corpus_fields, field_begin, n_fields, dim, q_vecs, Q, rows, C, out,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int mfar_union_rescore(const void* corpus, int64_t n_docs, int corpus_fields, int n_dense, int dim, const void* q_vecs,
+                       int Q, const float* w, const void* sparse, int n_sparse, int sparse_dtype, int64_t sparse_ld,
+                       const int64_t* cand_rows, int n_lists, int k_in, int k, float* out_scores, int64_t* out_rows,
+                       int32_t* out_union_size, void* stream) {
+  t_last_launches = 0;
+  if (!w || !cand_rows || !out_scores || !out_rows || !out_union_size || Q <= 0 || n_docs <= 0 || n_lists <= 0 ||
+      k_in <= 0)
+    return MFAR_ERR_ARG;
+  if (n_dense < 0 || n_sparse < 0 || n_dense + n_sparse <= 0 || n_dense + n_sparse > MFAR_MAX_FIELDS) return MFAR_ERR_SHAPE;
+  if (n_dense > 0 && (!corpus || !q_vecs || dim <= 0 || dim % 8 != 0 || n_dense > corpus_fields)) return MFAR_ERR_ARG;
+  if (n_sparse > 0 && (!sparse || sparse_ld < n_docs || (sparse_dtype != MFAR_F16 && sparse_dtype != MFAR_F32)))
+    return MFAR_ERR_ARG;
+  if (k <= 0 || k > MFAR_MAX_K || int64_t(n_lists) * k_in > 8192 || n_docs > (int64_t(1) << 32) - 2) return MFAR_ERR_SHAPE;
+  if (int rc = check_arch()) return rc;
+  if (int rc = launch_union_rescore(corpus, n_docs, corpus_fields, n_dense, dim, q_vecs, Q, w, n_dense + n_sparse, sparse,
+                                    sparse_dtype, sparse_ld, n_sparse, cand_rows, n_lists, k_in, k, out_scores, out_rows,
+                                    out_union_size, static_cast<cudaStream_t>(stream)))
+    return rc;
+  t_last_launches = 1;
+  return MFAR_OK;
 }
 
 // scratch layout for the host-buffer call

@@ -220,25 +220,56 @@ __device__ __forceinline__ uint64_t warp_compact_list(uint64_t* list, int count,
   return __shfl_sync(0xffffffffu, kth, (k - 1) >> 3);
 }
 
-// Cheaper compaction for every round after the first: instead of sorting, binary-search the 32-bit score word for
-// the largest T with count(score >= T) >= k (a warp-wide count per probe: 8 compares + one REDUX), stop as soon as
-// k <= count <= k + kSelectSlack, and keep exactly those keys (ballot-compacted, unsorted).  ~1/5 of the sort's
-// instructions.  Returns the admission threshold "(T << 32) - 1" (key > thr  <=>  score word >= T) and the new
-// count through *new_count.  Falls back to the exact sort when score ties keep too many keys.
+// Compaction by SELECTION instead of sorting: search the 32-bit score word for the largest T with
+// count(score >= T) >= k, stop as soon as k <= count <= k + kSelectSlack, and keep exactly those keys (ballot-compacted,
+// unsorted).  The search is 4-ary: three thresholds per round, their three warp-wide counts packed into ONE REDUX
+// (10 bits each: a list holds at most 256 keys), so a round costs 24 compares + 1 REDUX and the range shrinks 4x -
+// about half the dependent REDUX round trips of the bisection round 1 used (a compaction was ~9.4k cycles, of which
+// the two searches ~2.5k).  Returns the admission threshold "(T << 32) - 1" (key > thr  <=>  score word >= T) and the
+// new count through *new_count; the same search continued upwards for rank r <= k gives the pooled bound.  Falls back
+// to the exact sort when score ties keep too many keys.
 constexpr int kSelectSlack = 24;
 
-__device__ __forceinline__ uint64_t warp_select_list(uint64_t* list, int count, int k, int max_keep, int lane,
-                                                     int* new_count, int r, uint64_t* rank_r_bound) {
-  // max_keep: the caller's list may hold at most this many keys after compaction (its overflow trigger level)
-  const int slack = min(kSelectSlack, max_keep - k);
-  uint64_t v[8];
-  uint32_t hi[8];
+__device__ __forceinline__ void warp_list_load(const uint64_t* list, int count, int lane, uint64_t (&v)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int e = lane * 8 + j;
     v[j] = (e < count) ? __ldcg(list + e) : 0ull;
-    hi[j] = uint32_t(v[j] >> 32);                       // 0 for empty slots: below every real score word
   }
+}
+
+// largest T in [lo, up] with count(hi >= T) >= rank, given count(hi >= lo) >= rank; stops early once the count at the
+// running lower end is <= rank + slack (slack < 0: run to the exact answer).  *c_lo_io: count(hi >= lo) in / out.
+__device__ __forceinline__ uint32_t warp_rank_search(const uint32_t (&hi)[8], uint32_t lo, uint32_t up, int rank, int slack,
+                                                     int* c_lo_io) {
+  int c_lo = *c_lo_io;
+  while (lo < up && (slack < 0 || c_lo > rank + slack)) {
+    const uint32_t span = up - lo;                      // >= 1
+    const uint32_t m2 = lo + (span >> 1) + (span & 1u); // lo < m2 <= up
+    const uint32_t m1 = lo + ((m2 - lo) >> 1) + ((m2 - lo) & 1u);                 // lo < m1 <= m2
+    const uint32_t m3 = m2 + ((up - m2) >> 1) + ((up - m2) & 1u);                 // m2 <= m3 <= up
+    uint32_t c = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      c += (hi[j] >= m1 ? 1u : 0u) + (hi[j] >= m2 ? 1u << 10 : 0u) + (hi[j] >= m3 ? 1u << 20 : 0u);
+    c = __reduce_add_sync(0xffffffffu, c);
+    const int c1 = int(c & 1023u), c2 = int((c >> 10) & 1023u), c3 = int(c >> 20);
+    if (c3 >= rank) { lo = m3; c_lo = c3; }
+    else if (c2 >= rank) { lo = m2; c_lo = c2; up = m3 - 1u; }
+    else if (c1 >= rank) { lo = m1; c_lo = c1; up = m2 - 1u; }
+    else { up = m1 - 1u; }
+  }
+  *c_lo_io = c_lo;
+  return lo;
+}
+
+// v: the list's keys, 8 per lane (warp_list_load).  max_keep: the list may hold at most this many keys afterwards.
+__device__ __forceinline__ uint64_t warp_select_keys(const uint64_t (&v)[8], uint64_t* list, int count, int k, int max_keep,
+                                                     int lane, int* new_count, int r, uint64_t* rank_r_bound) {
+  const int slack = min(kSelectSlack, max_keep - k);
+  uint32_t hi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) hi[j] = uint32_t(v[j] >> 32);       // 0 for empty slots: below every real score word
   uint32_t mx = 0u, mn = 0xFFFFFFFFu;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -247,33 +278,31 @@ __device__ __forceinline__ uint64_t warp_select_list(uint64_t* list, int count, 
   }
   mx = __reduce_max_sync(0xffffffffu, mx);
   mn = __reduce_min_sync(0xffffffffu, mn);
-  uint32_t lo = mn, up = mx;                            // invariant: count(>= lo) >= k;  answer in [lo, up]
-  int c_lo = count;
-  while (lo < up && c_lo > k + slack) {
-    const uint32_t mid = lo + ((up - lo + 1u) >> 1);    // lo < mid <= up
-    int c = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) c += (hi[j] >= mid) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c >= k) { lo = mid; c_lo = c; } else { up = mid - 1u; }
-  }
+  int c_lo = count;                                     // invariant: count(>= lo) = c_lo >= k; answer in [lo, up]
+  const uint32_t lo = warp_rank_search(hi, mn, mx, k, slack, &c_lo);
   if (c_lo > k + slack) {                               // a big tie group straddles rank k (or no slack): exact path
     *new_count = k;
-    const uint64_t kth = warp_compact_list(list, count, k, lane);
-    __syncwarp();
-    *rank_r_bound = __ldcg(list + r - 1);               // sorted now: the exact rank-r key
-    return kth;
-  }
-  {                                                     // same search for rank r <= k on [lo, mx]: count(>= lo) >= k >= r
-    uint32_t lo2 = lo, up2 = mx;
-    while (lo2 < up2) {
-      const uint32_t mid = lo2 + ((up2 - lo2 + 1u) >> 1);
-      int c = 0;
+    uint64_t w[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) c += (hi[j] >= mid) ? 1 : 0;
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c >= r) lo2 = mid; else up2 = mid - 1u;
+    for (int j = 0; j < 8; ++j) w[j] = v[j];
+    warp_sort256_desc(w, lane);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = lane * 8 + j;
+      if (e < k) __stcg(list + e, w[j]);
     }
+    uint64_t kth = 0, rth = 0;                          // rank x lives in lane (x-1)/8, register (x-1)%8
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (((k - 1) & 7) == j) kth = w[j];
+      if (((r - 1) & 7) == j) rth = w[j];
+    }
+    *rank_r_bound = __shfl_sync(0xffffffffu, rth, (r - 1) >> 3);
+    return __shfl_sync(0xffffffffu, kth, (k - 1) >> 3);
+  }
+  {                                                     // same search for rank r <= k on [lo, mx], to the exact word
+    int c2 = c_lo;
+    const uint32_t lo2 = warp_rank_search(hi, lo, mx, r, -1, &c2);
     *rank_r_bound = (uint64_t(lo2) << 32) - 1ull;       // >= r keys have score word >= lo2, i.e. key > this bound
   }
   int base = 0;
@@ -286,6 +315,48 @@ __device__ __forceinline__ uint64_t warp_select_list(uint64_t* list, int count, 
   }
   *new_count = base;
   return (uint64_t(lo) << 32) - 1ull;
+}
+
+__device__ __forceinline__ uint64_t warp_select_list(uint64_t* list, int count, int k, int max_keep, int lane,
+                                                     int* new_count, int r, uint64_t* rank_r_bound) {
+  uint64_t v[8];
+  warp_list_load(list, count, lane, v);
+  return warp_select_keys(v, list, count, k, max_keep, lane, new_count, r, rank_r_bound);
+}
+
+// Pooled bounds, split so that the loads of the other CTAs' slots can be issued BEFORE the select of the list at hand
+// (their L2 round trip then hides behind the search): pool_load_others, later pool_publish_min.  Reading the others'
+// bounds a little early is harmless - every slot only ever grows, an older value is a weaker but still valid bound.
+constexpr int kPoolPerLane = 5;                         // up to 160 lists per query (148 CTAs, or 74 pairs x 2 sets)
+
+__device__ __forceinline__ void pool_load_others(const unsigned long long* pool, int G, int q_pad, int g, int q, int lane,
+                                                 unsigned long long (&pl)[kPoolPerLane]) {
+#pragma unroll
+  for (int i = 0; i < kPoolPerLane; ++i) {
+    const int gg = lane + 32 * i;
+    pl[i] = (gg < G && gg != g) ? ws_ld_relaxed_u64(pool + (long long)gg * q_pad + q) : ~0ull;
+  }
+}
+
+__device__ __forceinline__ unsigned long long pool_publish_min(unsigned long long* pool, int G, int q_pad, int g, int q,
+                                                               unsigned long long mine, int lane,
+                                                               const unsigned long long (&pl)[kPoolPerLane]) {
+  if (G > 32 * kPoolPerLane) return pool_publish_and_min(pool, G, q_pad, g, q, mine, lane);   // not prefetched
+  if (lane == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(pool + (long long)g * q_pad + q), "l"(mine) : "memory");
+  unsigned long long m = mine;
+#pragma unroll
+  for (int i = 0; i < kPoolPerLane; ++i) {
+#ifdef MFAR_FAULT_POOLED
+    if (pl[i] == 0ull) continue;
+#endif
+    m = pl[i] < m ? pl[i] : m;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long v = __shfl_xor_sync(0xffffffffu, m, o);
+    m = v < m ? v : m;
+  }
+  return m;
 }
 
 }  // namespace mfar

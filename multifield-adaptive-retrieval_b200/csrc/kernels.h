@@ -51,6 +51,11 @@ int launch_sparse_premix_coo(const int32_t* keys, const void* vals, int val_dtyp
 int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
                  int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
 int launch_zero_init(float* scores, int64_t* ids, int n, cudaStream_t st);
+// union of per-field candidate lists + gather-rescore + mixture + top-k for a whole batch (union_rescore.cu)
+int launch_union_rescore(const void* corpus, int64_t n_docs, int corpus_fields, int n_dense, int dim, const void* q_vecs,
+                         int Q, const float* w, int w_ld, const void* sparse, int sparse_dtype, int64_t sparse_ld,
+                         int n_sparse, const int64_t* cand, int L, int k_in, int k_out, float* out_scores,
+                         int64_t* out_rows, int* out_union, cudaStream_t st);
 int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
                           const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, int* epoch_dev,
                           uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
@@ -90,7 +95,15 @@ struct ScoreArgs {
   int n_sparse;
   int64_t doc_id_base;
   int k;
+  // optional per-query admission thresholds known before the pass starts (packed keys, [Q], 0 = none): copied into the
+  // workspace's shared threshold words right after they are zeroed (score_topk_core's prefix pass)
+  const unsigned long long* gthr_seed;
 };
+
+// gthr[q] = seed[q] (after the launcher zeroed the workspace tail)
+int launch_seed_gthr(unsigned long long* gthr, const unsigned long long* seed, int Q, cudaStream_t st);
+// seed[q] = keys[q, k-1] - 1 (the k-th best key of a prefix, made exclusive), 0 when the prefix holds fewer than k docs
+int launch_seed_from_keys(const uint64_t* keys, int Q, int k, unsigned long long* seed, cudaStream_t st);
 
 // SIMT (CUDA-core) scoring pass.  workers = grid size; fills ws candidate lists.
 int launch_score_simt(const ScoreArgs& a, void* ws_base, int workers, int q_pad, cudaStream_t st);

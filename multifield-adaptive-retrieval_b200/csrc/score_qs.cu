@@ -135,6 +135,54 @@ __device__ __forceinline__ void qs_sparse_consume(const uint8_t* slot, int qloc,
   }
 }
 
+// Compaction of the candidate lists of one epilogue warp (lane = query) that could overflow on the next unit, one list
+// at a time by the whole warp.  Every round is a warp SELECT (4-ary search on the score word; it also yields the
+// rank-r bound that is published).  The loop is software-pipelined over the lists: the keys of the NEXT list and the
+// other CTAs' pooled bounds of THIS list's query are requested before this list's select runs, so neither L2 round
+// trip sits on the critical path.  Deliberately NOT inlined: inlined, its ~30 extra live registers changed the
+// allocation of the drain / FMA loop around it and cost the 5-field MAG shape 7 % (2.71 -> 2.90 ms at Q=512).
+struct QsCompacted { uint64_t thr; int cnt; };
+
+__device__ __noinline__ QsCompacted qs_compact_lists(unsigned need, uint64_t* my_list, int cnt, int qrow, uint64_t thr,
+                                                     int lane, unsigned long long* pool, unsigned long long* gthr,
+                                                     int q_pad, int k, int GL, int gl) {
+  const int r = pooled_rank(k, GL);
+  uint64_t v_cur[8];
+  {
+    const int l0 = __ffs(need) - 1;
+    __syncwarp();                                    // the list's last pushes (this warp's own lanes) are visible
+    warp_list_load(my_list + int64_t(l0 - lane) * kCandCap, __shfl_sync(0xffffffffu, cnt, l0), lane, v_cur);
+  }
+  while (need) {
+    const int l = __ffs(need) - 1;
+    need &= need - 1;
+    const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
+    const int qrow_l = __shfl_sync(0xffffffffu, qrow, l);
+    uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
+    unsigned long long pl[kPoolPerLane];
+    pool_load_others(pool, GL, q_pad, gl, qrow_l, lane, pl);
+    uint64_t v_next[8];
+    if (need) {
+      const int ln = __ffs(need) - 1;
+      warp_list_load(my_list + int64_t(ln - lane) * kCandCap, __shfl_sync(0xffffffffu, cnt, ln), lane, v_next);
+    }
+    int cnt_new = k;
+    uint64_t bound_r = 0ull;
+    const uint64_t kth = warp_select_keys(v_cur, list_l, cnt_l, k, kCandCap - kQsDocs, lane, &cnt_new, r, &bound_r);
+    const unsigned long long pooled = pool_publish_min(pool, GL, q_pad, gl, qrow_l, bound_r, lane, pl);
+    if (lane == l) {
+      thr = kth > thr ? kth : thr;
+      thr = pooled > thr ? pooled : thr;
+      cnt = cnt_new;
+      atomicMax(gthr + qrow, thr);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v_cur[j] = v_next[j];
+    __syncwarp();
+  }
+  return QsCompacted{thr, cnt};
+}
+
 // SP: the epilogue gathers the sparse fields itself (qs_seed_sparse) - a separate instantiation, so the dense-only
 // kernels keep their register allocation
 template <int CG, int ES, bool SP>
@@ -428,6 +476,11 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         // accumulators start from the pre-mixed sparse term (16 x 16-byte loads per query row, issued ahead of the
         // wait for the half-tile's first accumulator; base_ld is a multiple of 128, so the row read stays in bounds)
         const bool sp_live = SP && doc0 < p.n_docs;   // warp-uniform: padding queries read TMA zero fill
+        // the best threshold any CTA found for this query: requested now, used after the half-tile's last field (an L2
+        // round trip that used to sit in front of every push phase)
+        const bool refresh = q_valid && ((n_push++ & refresh_mask) == 0);
+        unsigned long long gt_new = 0ull;
+        if (refresh) gt_new = ld_relaxed_u64(p.ws.gthr + qrow);
         int sp_e = 0;                                // next sparse element of this half-tile to consume
         if (sp_live) {
 #pragma unroll
@@ -473,10 +526,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
         // ---- 64 docs scored under every field: threshold filter, push
         // adopt the best threshold any CTA found for this query - an L2 round trip, so not more often than once
         // per ~8 MMA units (every half-tile when n_dense >= 8, every 8th for a single_ scorer)
-        if (q_valid && ((n_push++ & refresh_mask) == 0)) {
-          const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + qrow);
-          thr = gt > thr ? gt : thr;                                     // incl. the pooled bound, common.cuh
-        }
+        thr = gt_new > thr ? gt_new : thr;                               // incl. the pooled bound, common.cuh
         if (q_valid && doc0 < p.n_docs) {
           const int64_t left = p.n_docs - doc0;
           const int nd = left < kQsDocs ? int(left) : kQsDocs;
@@ -509,29 +559,11 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
 #ifdef MFAR_QS_TIMING
         n_compact += __popc(need);
 #endif
-        while (need) {
-          const int l = __ffs(need) - 1;
-          need &= need - 1;
-          const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
-          uint64_t* list_l = my_list + int64_t(l - lane) * kCandCap;
-          __syncwarp();
-          // every round is a warp SELECT (binary search on the score word; it also yields the rank-r bound that is
-          // published) - the exact bitonic sort the first round used to run cost ~5x more, a fixed ~0.25 ms per launch
-          // (128 lists per CTA) that mid-size shards (MAG 700k docs, the 8-GPU shards) paid in full
-          int cnt_new = p.k;
-          const int r = pooled_rank(p.k, GL);
-          uint64_t bound_r = 0ull;
-          const uint64_t kth = warp_select_list(list_l, cnt_l, p.k, kCandCap - kQsDocs, lane, &cnt_new, r, &bound_r);
-          __syncwarp();
-          const int qrow_l = __shfl_sync(0xffffffffu, qrow, l);
-          const unsigned long long pooled = pool_publish_and_min(p.ws.pool, GL, p.ws.q_pad, gl, qrow_l, bound_r, lane);
-          if (lane == l) {
-            thr = kth > thr ? kth : thr;
-            thr = pooled > thr ? pooled : thr;
-            cnt = cnt_new;
-            atomicMax(p.ws.gthr + qrow, thr);
-          }
-          __syncwarp();
+        if (need) {
+          const QsCompacted c = qs_compact_lists(need, my_list, cnt, qrow, thr, lane, p.ws.pool, p.ws.gthr, p.ws.q_pad,
+                                                 p.k, GL, gl);
+          thr = c.thr;
+          cnt = c.cnt;
         }
         QS_ETICK(e_compact)
       }
@@ -639,6 +671,7 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   }));
   // lockstep counters of the query groups (producer warp) + shared per-query thresholds (epilogue)
   MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));
+  if (a.gthr_seed) { if (int rc2 = launch_seed_gthr(p.ws.gthr, a.gthr_seed, a.Q, st)) return rc2; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(q_tiles, workers);
   cfg.blockDim = dim3(qs_threads(ES, SP));

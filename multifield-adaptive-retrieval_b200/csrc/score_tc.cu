@@ -439,6 +439,7 @@ static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
     return cudaFuncSetAttribute(score_tc_kernel<QP, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_cap));
   }));
   MFAR_CUDA_OK(cudaMemsetAsync(p.ws.progress, 0, workspace_zero_bytes(p.ws.workers, p.ws.q_pad), st));   // shared thresholds
+  if (a.gthr_seed) { if (int rc2 = launch_seed_gthr(p.ws.gthr, a.gthr_seed, a.Q, st)) return rc2; }
   dim3 grid(workers, q_tiles);
   score_tc_kernel<QP, SP><<<grid, SP ? kTcThreads + kStagerThreads : kTcThreads, smem, st>>>(map_a, map_b, p);
   MFAR_CUDA_OK(cudaGetLastError());

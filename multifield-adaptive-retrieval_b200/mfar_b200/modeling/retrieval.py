@@ -488,19 +488,23 @@ class MultiFieldRetriever:
         Q = self._batch_size(q_bf16, sparse, None, batch)
         sp, code = self._check_sparse(sparse, Q)
         ones = torch.ones((Q, 1), dtype=torch.float32, device=self.device)
-        all_s, all_i = [], []
+        all_s, all_i, launches = [], [], 0
         for f in range(self.n_dense):
             s, i, _ = self._score_topk(q_bf16, ones, None, nv.F16, k, f, 1, 0)
+            launches += self.last_launches
             i = i - self.doc_id_base
             if zero_init:
                 nv.check(nv.lib().mfar_topk_apply_zero_init(nv.ptr(s), nv.ptr(i), Q, k, nv.stream()), "zero_init")
+                launches += 1
             all_s.append(s)
             all_i.append(i)
         for j in range(self.n_sparse):
             sj = sp[:, j:j + 1, :].contiguous()
             s, i, _ = self._score_topk(None, ones, sj, code, k, 0, 0, 1)
+            launches += self.last_launches
             all_s.append(s)
             all_i.append(i - self.doc_id_base)
+        self.last_launches = launches
         return torch.stack(all_s), torch.stack(all_i)
 
     # ------------------------------------------------------------------ candidate re-scoring (index.py:227-232)
@@ -528,35 +532,51 @@ class MultiFieldRetriever:
 
     # ------------------------------------------------------------------ faithful pipeline (contrastive.py:669-704)
     @torch.no_grad()
+    def union_rescore_batch(self, q_vecs, q_emb: Optional[torch.Tensor] = None, sparse: Optional[torch.Tensor] = None,
+                            top_k: Optional[int] = None, sparse_tokens=None, batch: Optional[int] = None
+                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """The reference pipeline for a whole batch on the device: per-field top-k (one streaming pass per field,
+        ``retrieve_batch``, contrastive.py:672-674) then ONE kernel (``mfar_union_rescore``) for per-query union ->
+        rescore under every field -> * mask -> mixture -> top-k (676-696).
+        Returns (values [Q,k], local rows [Q,k], union sizes [Q]); rows of a query whose union is smaller than k are
+        padded with (-inf, -1) - ``union_rescore`` raises for those, like the reference's ``torch.topk``."""
+        k = top_k or self.top_k
+        q_bf16 = self.corpus.prepare_queries(q_vecs) if self.corpus is not None else None
+        if sparse_tokens is not None:                                      # BM25 get_scores once per (query, field)
+            sparse = self._sparse_from_tokens(None, sparse_tokens, q_bf16, batch)
+        _, rows = self.per_field_topk(q_vecs, sparse, k, batch=batch)      # [F,Q,k] local rows, (0.0, row 0) quirk applied
+        Q = rows.shape[1]
+        if self.mixture.query_cond:
+            qv = q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs)
+            qe = (q_emb if q_emb is not None else qv).to(self.device).float()
+        else:
+            qe = None
+        w = self.mixture.field_weights(qe, self.mask, batch=Q)             # softmax(q@W) * mask, [Q,F]
+        sp, code = self._check_sparse(sparse, Q)
+        vals = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        out_rows = torch.empty((Q, k), dtype=torch.int64, device=self.device)
+        usize = torch.empty((Q,), dtype=torch.int32, device=self.device)
+        c = self.corpus
+        rows = rows.contiguous()
+        nv.check(nv.lib().mfar_union_rescore(
+            nv.ptr(c.data) if c is not None else 0, self.n_docs, c.n_fields if c is not None else 0, self.n_dense,
+            c.dim_pad if c is not None else 0, nv.ptr(q_bf16), Q, nv.ptr(w), nv.ptr(sp), self.n_sparse, code,
+            sp.shape[2] if sp is not None else self.n_docs, nv.ptr(rows), rows.shape[0], rows.shape[2], k, nv.ptr(vals),
+            nv.ptr(out_rows), nv.ptr(usize), nv.stream()), "union_rescore")
+        self.last_launches += 2                                            # + mixture weights + the union/rescore kernel
+        return vals, out_rows, usize
+
+    @torch.no_grad()
     def union_rescore(self, q_vecs, q_emb: Optional[torch.Tensor] = None, sparse: Optional[torch.Tensor] = None,
-                      top_k: Optional[int] = None, sparse_tokens=None
+                      top_k: Optional[int] = None, sparse_tokens=None, batch: Optional[int] = None
                       ) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
-        """per-field top-k -> union -> rescore -> * mask -> mixture -> top-k, per query.
+        """per-field top-k -> union -> rescore -> * mask -> mixture -> top-k (``union_rescore_batch``).
         Returns per query (values [k], local rows [k])."""
         k = top_k or self.top_k
-        if sparse_tokens is not None:                                      # BM25 get_scores once per (query, field)
-            sparse = self._sparse_from_tokens(None, sparse_tokens,
-                                              None if self.corpus is None else self.corpus.prepare_queries(q_vecs))
-        _, rows = self.per_field_topk(q_vecs, sparse, k)                   # [F,Q,k]
-        Q = rows.shape[1]
-        qv = q_vecs if torch.is_tensor(q_vecs) else torch.from_numpy(q_vecs)
-        qe = (q_emb if q_emb is not None else qv).to(self.device).float()
-        out_v, out_r = [], []
-        for i in range(Q):
-            union = torch.unique(rows[:, i, :].reshape(-1))               # sorted ascending
-            per_field = self.score_candidates(qv[i:i + 1], union, None if sparse is None else sparse[i:i + 1])
-            all_tens = per_field.squeeze(1) * self.mask                   # [F,U] * [F,1]   contrastive.py:686
-            scores = self.mixture(all_tens.t().contiguous(), qe[i:i + 1] if self.mixture.query_cond else None)
-            if scores.shape[1] < k:
-                raise RuntimeError("selected index k out of range")       # what torch.topk raises in the reference
-            # final top-k of the mixed union scores (contrastive.py:696) with the same streaming top-k kernel:
-            # the [1,U] score row is fed as a single pre-scored "field" of a U-doc shard
-            vals, idx, _ = self._score_topk(None, torch.ones((1, 1), dtype=torch.float32, device=self.device),
-                                            scores.reshape(1, 1, -1).contiguous(), nv.F32, k, 0, 0, 1,
-                                            n_docs=scores.shape[1], doc_id_base=0)
-            out_v.append(vals[0])
-            out_r.append(union[idx[0]])
-        return out_v, out_r
+        vals, rows, usize = self.union_rescore_batch(q_vecs, q_emb, sparse, k, sparse_tokens, batch)
+        if int(usize.min().item()) < k:
+            raise RuntimeError("selected index k out of range")           # what torch.topk raises in the reference
+        return list(vals.unbind(0)), list(rows.unbind(0))
 
     # ------------------------------------------------------------------ QRes emission (contrastive.py:696-704)
     def trec_eval_step(self, query_ids: Sequence[str], q_vecs, qres_output: TextIO, q_emb=None, sparse=None,

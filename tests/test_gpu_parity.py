@@ -296,6 +296,39 @@ def test_union_rescore_vs_reference_pipeline(path):
             assert (np.abs(ref_v - ref_v[j]) <= 1e-5 * max(1.0, np.abs(ref_v).max())).sum() > 1
 
 
+@pytest.mark.parametrize("shape", [(81, 5000, 768, 3, 2, 70, True, 100), (82, 3000, 256, 8, 0, 9, False, 100),
+                                   (83, 2000, 128, 1, 3, 33, True, 50), (84, 900, 64, 0, 4, 5, False, 20),
+                                   (85, 700, 64, 22, 22, 3, True, 20)], ids=lambda s: f"s{s[0]}")
+def test_union_rescore_batch_on_device_vs_oracle_pipeline(shape):
+    """The whole candidate stage of trec_eval_step (contrastive.py:676-696) in one launch for the batch
+    (``mfar_union_rescore``) against the oracle's per-query restatement: same union sizes, same values, same rows up to
+    near-ties; a masked field; more sparse than dense fields; sparse-only; 44 fields."""
+    seed, N, d, Fd, Fs, Q, qc, k = shape
+    fields, q, sp, W = synth(seed, N, d, Fd, Fs, Q, qc)
+    r = build(fields, W, qc, Fs, k, n_docs=N)
+    mask = torch.ones(Fd + Fs, 1)
+    if Fd + Fs > 2:
+        mask[1] = 0
+        r.mask_field([1])
+    qd = q.to(DEV)
+    vals, rows, usize = r.union_rescore_batch(qd if Fd else None, qd, None if sp is None else sp.to(DEV), k,
+                                              batch=Q)
+    ref_v, ref_r = O.union_rescore(q, fields, None if sp is None else sp.float(), q, W, qc, mask, k)
+    # union sizes: recompute from the oracle's per-field lists
+    hits = [O.dense_retrieve_batch(q, f, k)[1] for f in fields] + \
+           ([O.sparse_retrieve_batch(sp[:, j, :].float(), k)[1] for j in range(Fs)] if Fs else [])
+    for i in range(Q):
+        want_u = len(set().union(*[set(h[i].tolist()) for h in hits]))
+        assert abs(int(usize[i]) - want_u) <= 2, (i, int(usize[i]), want_u)      # near-ties at a field's k-th place
+        np.testing.assert_allclose(vals[i].cpu().numpy(), ref_v[i].numpy(), rtol=2e-5, atol=1e-5)
+        got_r, want_r = rows[i].cpu().numpy(), np.asarray(ref_r[i])
+        rv = ref_v[i].numpy()
+        for j in np.nonzero(got_r != want_r)[0]:
+            assert (np.abs(rv - rv[j]) <= 1e-5 * max(1.0, np.abs(rv).max())).sum() > 1, (i, j)
+    lv, lr = r.union_rescore(qd if Fd else None, qd, None if sp is None else sp.to(DEV), k, batch=Q)
+    assert len(lv) == Q and torch.equal(lv[0], vals[0]) and torch.equal(lr[-1], rows[-1])
+
+
 def test_search_host_equals_device_search_and_counts_launches():
     fields, q, sp, W = synth(31, 1000, 768, 3, 2, 9, True)
     r = build(fields, W, True, 2, 100)

@@ -32,3 +32,6 @@ for o in d.get("other_workloads", []):
     print(f"  {o['workload']} ({o['n_docs']} docs, {o['n_dense']}+{o['n_sparse']} fields, shard {o['shard_docs']})  parity ok={pc.get('ok')} q={pc.get('queries')} {pc.get('error', '')}")
     for b in o["batches"]:
         row(b, "    ")
+    u = o.get("union_rescore")
+    if u:
+        print("    union_rescore:", {k: (round(v, 3) if isinstance(v, float) else v) for k, v in u.items() if k != "mode"})
