@@ -376,11 +376,16 @@ class Workload:
             nv.check(nv.lib().mfar_profile_enable(1))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches = 0
+        ncu_range = os.environ.get("MFAR_NCU_RANGE") == "1"      # ncu --profile-from-start off: timed regions only
+        if ncu_range:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(steps):
             launches += self.step(pool[i % len(pool)], graph)[1]
         e1.record()
         ctx.barrier()
+        if ncu_range:
+            torch.cuda.profiler.stop()
         ms = ctx.max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if sampler else None
         kern_ms = []
