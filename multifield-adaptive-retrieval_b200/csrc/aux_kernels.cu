@@ -397,16 +397,20 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
 // ---------------------------------------------------------------------------------------
 // Cross-GPU exchange + merge in ONE kernel over NVLink peer memory (replaces ncclAllGather + merge).
 // Every rank owns a buffer [flags: 2][world][q_cap] i32 | [keys: 2][world][q_cap][k_cap] u64 that all peers have
-// mapped (CUDA VMM / torch symmetric memory).  One CTA per query:
-//   1. PUSH   the rank's local top-k keys of this query into slot [parity][rank][q] of EVERY rank's buffer
-//             (st.global on peer-mapped addresses -> NVLink), then, after a system-scope fence, the flag = epoch;
-//   2. WAIT   until the flags of all ranks for this query show `epoch` in the LOCAL buffer (ld.acquire.sys);
-//   3. MERGE  the world * k_in keys (now local) with the block bitonic sort and emit the global top-k.
-// Buffers alternate by epoch parity: a peer can only be one call ahead (it needs this rank's next push to finish
-// its next call), so two slots are enough.  CTAs push before they wait and are scheduled in query order on every
-// rank, so the resident CTAs of all ranks always contain the lowest unfinished query: no deadlock.
+// mapped (CUDA VMM / torch symmetric memory).  A grid of min(Q, 296) CTAs - all co-resident (2 per SM) - walks the
+// queries b, b + grid, ... in TWO sweeps:
+//   1. PUSH   for each of its queries, the rank's local top-k keys go into slot [parity][rank][q] of EVERY rank's
+//             buffer (st.global on peer-mapped addresses -> NVLink) and, after a system-scope fence, the flag = epoch;
+//   2. WAIT + MERGE  for each of its queries, until the flags of all ranks show `epoch` in the LOCAL buffer
+//             (ld.acquire.sys), then the world * k_in keys (now local) are ranked by the block bitonic sort.
+// No CTA waits before it has pushed everything it owns, and every CTA of the grid is resident, so every push of every
+// rank is issued regardless of how the hardware orders CTAs: the wait always terminates once all ranks have launched
+// (round 1 used one CTA per query and relied on CTAs being scheduled in index order when Q exceeded the resident
+// capacity).  Buffers alternate by epoch parity: a peer can only be one call ahead (it needs this rank's next push to
+// finish its next call), so two slots are enough.
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
+constexpr int kExchangeMaxCtas = 2 * kNumSmsB200;
 struct PeerBufs { unsigned long long base[kMaxPeers]; };
 
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
@@ -418,57 +422,62 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kMergeThreads)
-exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int k_in, PeerBufs peers, int rank, int world, int q_cap,
-                      int k_cap, int epoch_arg, const int* __restrict__ epoch_dev, int k, uint64_t* __restrict__ out_keys,
-                      float* __restrict__ out_scores, int64_t* __restrict__ out_ids, int* __restrict__ err) {
+__global__ void __launch_bounds__(kMergeThreads, 2)
+exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int Q, int k_in, PeerBufs peers, int rank, int world,
+                      int q_cap, int k_cap, int epoch_arg, const int* __restrict__ epoch_dev, int k,
+                      uint64_t* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                      int* __restrict__ err) {
   __shared__ uint64_t buf[kMergeBuf];
-  const int q = blockIdx.x, t = threadIdx.x;
+  const int t = threadIdx.x;
   // the call counter: a kernel argument, or - so that the launch can be replayed from a CUDA graph - a device word
   // that bump_epoch_kernel (same stream, just before this kernel) increments
   const int epoch = epoch_dev ? *epoch_dev : epoch_arg;
   const int parity = epoch & 1;
   const size_t flag_bytes = size_t(2) * world * q_cap * sizeof(int);
-  const size_t slot = (size_t(parity) * world + rank) * q_cap + q;            // [parity][rank][q]
-  // 1. push
-  for (int i = t; i < world * k_in; i += kMergeThreads) {
-    const int r = i / k_in, j = i % k_in;
-    uint64_t* dst = reinterpret_cast<uint64_t*>(peers.base[r] + flag_bytes) + slot * k_cap + j;
-    *dst = __ldg(local_keys + int64_t(q) * k_in + j);
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (t < world) st_release_sys(reinterpret_cast<int*>(peers.base[t]) + slot, epoch);
-  // 2. wait (bounded: a peer that never arrives becomes an error, not a hang)
-  if (t < world) {
-    const int* f = reinterpret_cast<const int*>(peers.base[rank]) + (size_t(parity) * world + t) * q_cap + q;
-    const unsigned long long t0 = clock64();
-    while (ld_acquire_sys(f) != epoch) {
-      if (clock64() - t0 > 20000000000ull) {                                  // ~10 s
-        atomicExch(err, 31);
-        __threadfence_system();
-        asm volatile("trap;");
-      }
-      __nanosleep(100);
-    }
-  }
-  __syncthreads();
-  // 3. merge (all data is in this rank's own buffer now)
-  const uint64_t* mine = reinterpret_cast<const uint64_t*>(peers.base[rank] + flag_bytes);
-  for (int i = t; i < kMergeBuf; i += kMergeThreads) {
-    uint64_t key = 0ull;
-    if (i < world * k_in) {
+  // 1. push everything this CTA owns
+  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+    const size_t slot = (size_t(parity) * world + rank) * q_cap + q;          // [parity][rank][q]
+    for (int i = t; i < world * k_in; i += kMergeThreads) {
       const int r = i / k_in, j = i % k_in;
-      key = __ldcg(mine + ((size_t(parity) * world + r) * q_cap + q) * k_cap + j);
+      uint64_t* dst = reinterpret_cast<uint64_t*>(peers.base[r] + flag_bytes) + slot * k_cap + j;
+      *dst = __ldg(local_keys + int64_t(q) * k_in + j);
     }
-    buf[i] = key;
+    __threadfence_system();
+    __syncthreads();
+    if (t < world) st_release_sys(reinterpret_cast<int*>(peers.base[t]) + slot, epoch);
   }
-  block_sort1024_desc(buf);
-  for (int j = t; j < k; j += kMergeThreads) {
-    const uint64_t key = buf[j];
-    if (out_keys) out_keys[int64_t(q) * k + j] = key;
-    if (out_scores) out_scores[int64_t(q) * k + j] = key ? key_score(key) : -INFINITY;
-    if (out_ids) out_ids[int64_t(q) * k + j] = key ? int64_t(key_doc(key)) : int64_t(-1);
+  // 2. wait (bounded: a peer that never arrives becomes an error, not a hang) and merge
+  const uint64_t* mine = reinterpret_cast<const uint64_t*>(peers.base[rank] + flag_bytes);
+  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+    if (t < world) {
+      const int* f = reinterpret_cast<const int*>(peers.base[rank]) + (size_t(parity) * world + t) * q_cap + q;
+      const unsigned long long t0 = clock64();
+      while (ld_acquire_sys(f) != epoch) {
+        if (clock64() - t0 > 20000000000ull) {                                // ~10 s
+          atomicExch(err, 31);
+          __threadfence_system();
+          asm volatile("trap;");
+        }
+        __nanosleep(100);
+      }
+    }
+    __syncthreads();
+    for (int i = t; i < kMergeBuf; i += kMergeThreads) {                      // all data is in this rank's own buffer now
+      uint64_t key = 0ull;
+      if (i < world * k_in) {
+        const int r = i / k_in, j = i % k_in;
+        key = __ldcg(mine + ((size_t(parity) * world + r) * q_cap + q) * k_cap + j);
+      }
+      buf[i] = key;
+    }
+    block_sort1024_desc(buf);
+    for (int j = t; j < k; j += kMergeThreads) {
+      const uint64_t key = buf[j];
+      if (out_keys) out_keys[int64_t(q) * k + j] = key;
+      if (out_scores) out_scores[int64_t(q) * k + j] = key ? key_score(key) : -INFINITY;
+      if (out_ids) out_ids[int64_t(q) * k + j] = key ? int64_t(key_doc(key)) : int64_t(-1);
+    }
+    __syncthreads();                                                          // buf is reused by the next query
   }
 }
 
@@ -630,8 +639,9 @@ int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, in
   int* err = reinterpret_cast<int*>(pb.base[rank] + size_t(2) * world * q_cap * sizeof(int) +
                                     size_t(2) * world * q_cap * k_cap * sizeof(uint64_t));
   if (epoch_dev) bump_epoch_kernel<<<1, 1, 0, st>>>(epoch_dev);
-  exchange_merge_kernel<<<Q, kMergeThreads, 0, st>>>(local_keys, k_in, pb, rank, world, q_cap, k_cap, epoch, epoch_dev, k,
-                                                     out_keys, out_scores, out_ids, err);
+  const int ctas = Q < kExchangeMaxCtas ? Q : kExchangeMaxCtas;               // all resident: 2 x 512 threads per SM
+  exchange_merge_kernel<<<ctas, kMergeThreads, 0, st>>>(local_keys, Q, k_in, pb, rank, world, q_cap, k_cap, epoch,
+                                                        epoch_dev, k, out_keys, out_scores, out_ids, err);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }
