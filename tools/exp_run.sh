@@ -1,6 +1,5 @@
-ncu --set full --clock-control none --import-source on -k regex:score_qs -s 4 -c 2 -o gpurun_out/r2m_qs_10m_q512 -f python bench.py --steps 2 --warmup 3 --others none --extra-batches "" --cpu-budget-s 0 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:score_qs -s 4 -c 2 -o gpurun_out/r2m_qs_amazon_q512 -f python tools/quick_bench.py --workload amazon_full --batches 512 --iters 2 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:score_tc -s 4 -c 2 -o gpurun_out/r2m_tc_amazon_q64 -f python tools/quick_bench.py --workload amazon_full --batches 64 --iters 2 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:score_qs -s 4 -c 2 -o gpurun_out/r2m_qs_mag_q512 -f python tools/quick_bench.py --workload mag_full --batches 512 --iters 2 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:score_tc -s 0 -c 1 -o gpurun_out/r2m_tc_10m_q1 -f python tools/quick_bench.py --workload scale_10m_all --batches 1 --iters 1 > /dev/null 2>&1
-ls -la gpurun_out/*.ncu-rep
+timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -k "peer_exchange or virtual" 2>&1 | tail -3
+MFAR_NCU_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2n_launches.csv python bench.py --steps 3 --warmup 3 --others amazon_full:64:512 --cpu-budget-s 0 > gpurun_out/r2n_under_ncu.json 2> /dev/null
+timeout 150 python tools/fuzz_parity.py --mode kernels --seconds 100 --seed 21 --out gpurun_out/r2n_fuzz_kernels.json 2>&1 | tail -3
+timeout 120 python tools/fuzz_parity.py --mode api --seconds 70 --seed 22 --out gpurun_out/r2n_fuzz_api.json 2>&1 | tail -3
+timeout 100 python tools/fuzz_parity.py --mode bm25 --seconds 50 --seed 23 --out gpurun_out/r2n_fuzz_bm25.json 2>&1 | tail -3
