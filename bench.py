@@ -202,6 +202,7 @@ class Ctx:
             else:
                 self.exchange_kind = "nccl all_gather + merge kernel"
         self.peaks = load_peaks()
+        self.pipelined = self.exchange is not None and args.exchange_mode == "pipelined"
         self.weights = [1.0] * self.world             # relative docs/s of every rank (calibrated when --balance)
         self.balance_note = "equal doc ranges"
 
@@ -217,15 +218,23 @@ class Ctx:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return t.item()
 
-    def calibrate(self, n_dense, Q, seconds=0.7):
-        """Speed-weighted shards: every step ends in an exchange that waits for the slowest rank, and the GPUs of a node
-        settle at different clocks under the 1 kW cap (a few per cent apart, persistently).  Each rank times the scoring
-        kernel on an identical 128k-doc calibration shard for `seconds` of sustained load; doc ranges are then sized in
-        proportion to the measured docs/s."""
+    def per_rank(self, x: float):
+        if self.world == 1:
+            return [x]
+        t = torch.zeros(self.world, device=self.device, dtype=torch.float64)
+        t[self.rank] = x
+        self.dist.all_reduce(t)
+        return t.tolist()
+
+    def calibrate(self, n_dense, Q, shard_docs, seconds=1.0):
+        """Speed-weighted shards: the job runs at the pace of its slowest rank, and the GPUs of a node settle at different
+        clocks under the 1 kW cap (a few per cent apart).  Each rank times the scoring kernel on an identical calibration
+        shard of the REAL shard size (so the kernel is in the same power-capped regime as in the run; capped at 2.5M docs)
+        for `seconds` of sustained load; doc ranges are then sized in proportion to the measured docs/s."""
         from mfar_b200 import synth
         from mfar_b200.modeling.retrieval import MultiFieldRetriever, PackedCorpus
         from mfar_b200.modeling.weighting import LinearWeights
-        n = 131072
+        n = int(min(max(shard_docs, 131072), 2_500_000))
         pc = PackedCorpus(n, max(n_dense, 1), DIM, self.device)
         synth.fill_packed_corpus(pc, seed=99)
         mu = synth.corpus_mean(DIM, 99, self.device)
@@ -241,11 +250,11 @@ class Ctx:
         while time.perf_counter() < t_end:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(20):
+            for _ in range(10):
                 r.search(q, qe)
             e1.record()
             e1.synchronize()
-            laps.append(e0.elapsed_time(e1) / 20)
+            laps.append(e0.elapsed_time(e1) / 10)
         mine = statistics.median(laps[len(laps) // 2:])          # the settled second half
         t = torch.zeros(self.world, device=self.device, dtype=torch.float64)
         t[self.rank] = mine
@@ -312,7 +321,10 @@ class Workload:
         self.retr = MultiFieldRetriever(self.pc, self.layer, n_sparse=self.n_sparse, top_k=TOPK, doc_id_base=self.lo,
                                         impl=a.kernel, sparse_indices=self.bm25_fields, n_docs=self.hi - self.lo,
                                         device=ctx.device)
-        self.sharded = ShardedRetriever(self.retr, exchange=ctx.exchange)
+        self.sharded = ShardedRetriever(self.retr, exchange=ctx.exchange)               # complete exchange per call
+        # throughput mode of the timed loops: a step pushes its keys and merges the PREVIOUS step's, so no rank waits
+        # for the slowest rank of the current step (results trail by one step; flush() returns the last one)
+        self.piped = ShardedRetriever(self.retr, exchange=ctx.exchange, pipelined=ctx.pipelined)
         self.setup_s = time.perf_counter() - t0
         self.graphs = {}
 
@@ -351,13 +363,13 @@ class Workload:
                 gs = self.graphs[key] = GraphedSearch(
                     self.retr, qv.shape[0], sparse="bm25" if self.bm25_mode else ("dense" if self.n_sparse else "none"),
                     max_entries=0 if ent is None else ent.shape[0], sparse_buffer=sp,
-                    sharded=self.sharded if self.ctx.world > 1 else None)
+                    sharded=self.piped if self.ctx.world > 1 else None)
             out = gs(qv, qe, sparse=sp, entries=ent)
             return out, gs.launches
-        out = self.sharded.search(qv, qe, sp, sparse_tokens=ent) if self.ctx.world > 1 else \
+        out = self.piped.search(qv, qe, sp, sparse_tokens=ent) if self.ctx.world > 1 else \
             self.retr.search(qv, qe, sp, sparse_tokens=ent)
-        extra = 1 + (2 if self.ctx.world > 1 and self.ctx.exchange is not None else (1 if self.ctx.world > 1 else 0))
-        return out, self.retr.last_launches + extra       # + mixture weights (+ epoch bump + exchange / merge)
+        extra = 1 + (0 if self.ctx.world == 1 else (1 if self.ctx.exchange is None else (3 if self.piped.pipelined else 2)))
+        return out, self.retr.last_launches + extra       # + mixture weights (+ epoch bump + exchange kernels / merge)
 
     def time_device(self, pool, steps, warmup, graph: bool, profile: bool, sample_clocks=False):
         """K timed steps with device-resident inputs.  Returns (ms total [max over ranks], launches, kernel ms list,
@@ -386,7 +398,9 @@ class Workload:
         ctx.barrier()
         if ncu_range:
             torch.cuda.profiler.stop()
-        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        ms_local = e0.elapsed_time(e1)
+        ms = ctx.max_over_ranks(ms_local)
+        self.last_per_rank_ms_per_step = [x / steps for x in ctx.per_rank(ms_local)]
         clocks = sampler.stop() if sampler else None
         kern_ms = []
         if prof:
@@ -400,6 +414,7 @@ class Workload:
                 self.step(pool[i % len(pool)], False)
             ctx.barrier()
             kern_ms = self._collect_profile()
+        self.last_per_rank_kernel_ms = ctx.per_rank(statistics.mean(kern_ms) if kern_ms else 0.0)
         return ms, launches, kern_ms, clocks
 
     @staticmethod
@@ -525,6 +540,14 @@ class Workload:
                 res["fused_exchange_equals_nccl_path"] = same
                 if not same:
                     raise AssertionError("fused exchange result differs from all_gather + merge")
+                if self.piped.pipelined:                  # the pipelined exchange delivers the same lists, one call later
+                    self.piped.search(qv, qe, sp, sparse_tokens=ent)
+                    s3, i3 = self.piped.search(qv, qe, sp, sparse_tokens=ent)          # = result of the first call
+                    s4, i4 = self.piped.flush()                                        # = result of the second call
+                    same = bool(torch.equal(s3, s) and torch.equal(i3, ids) and torch.equal(s4, s) and torch.equal(i4, ids))
+                    res["pipelined_exchange_equals_complete"] = same
+                    if not same:
+                        raise AssertionError("pipelined exchange result differs from the complete exchange")
             if self.bm25_mode:                            # BM25 scores are produced on the device: no independent rows
                 res.update({"ok": True, "note": "checker skipped for device-BM25 sparse fields"})
                 return res
@@ -609,13 +632,18 @@ def run_workload(ctx: Ctx, name, batches, steps, warmup, headline=False):
         k_ms = statistics.mean(km) if km else None
         rec = {"batch": Q, "value": Q * st / (ms * 1e-3), "ms_per_step": ms / st, "steps": st,
                "roofline": wl.roofline(Q, k_ms, len(km), ms, st), "gpu_launches": launches}
+        if ctx.world > 1:
+            rec["per_rank"] = {"ms_per_step": wl.last_per_rank_ms_per_step, "kernel_ms": wl.last_per_rank_kernel_ms,
+                               "note": "ms_per_step: each rank's own CUDA-event time of the timed loop / steps (the line's "
+                                       "ms_per_step is their maximum); kernel_ms: each rank's mean scoring-kernel time"}
         if main:
             rec["clocks"] = clocks
             ms_e, h2d, d2h = wl.time_e2e(pool, st, warmup, graph)
             rec["e2e"] = {"value": Q * st / (ms_e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d,
                           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / st,
                           "path": "mfar_search_host (C ABI, pinned host buffers)" if ctx.world == 1 else
-                                  "pinned host -> device copies + sharded step (graph replay) + D2H of the merged top-k"}
+                                  "pinned host -> device copies + sharded step (graph replay) + D2H of the merged top-k"
+                                  + (" of the previous step (pipelined exchange)" if ctx.pipelined else "")}
         if Q == max(batches):                          # check the largest batch (up to 4 of its queries)
             out["parity_check"] = wl.parity_check(pool[0])
         out["batches"].append(rec)
@@ -652,6 +680,9 @@ def main():
                     help="N=1: replay the device-resident step as one CUDA graph (always on for N>1)")
     ap.add_argument("--balance", default="auto", choices=["auto", "off"],
                     help="N>1: size the doc ranges by each GPU's measured speed (auto) or equally (off)")
+    ap.add_argument("--exchange-mode", default="complete", choices=["pipelined", "complete"],
+                    help="N>1 timed loops: a step merges the previous step's keys (pipelined, no waiting for the slowest "
+                         "rank of the step) or its own (complete)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="0 skips the cpu_baseline leg of our arm")
     ap.add_argument("--seed", type=int, default=1234)
     args = ap.parse_args()
@@ -702,7 +733,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA sm_100 device (there is no CPU fallback for the product path)")
     ctx = Ctx(args)
     if world > 1 and args.balance == "auto" and n_dense:
-        ctx.calibrate(n_dense, Q)
+        ctx.calibrate(n_dense, Q, n_total // world)
     config["sharding"] = f"doc-range x{world}, {ctx.balance_note}"
 
     extra = [int(x) for x in args.extra_batches.split(",") if x and int(x) != Q]
@@ -739,7 +770,10 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
             "roofline": main_rec["roofline"], "cpu_baseline": cpu_base, "e2e": main_rec["e2e"],
             "parity_check": head["parity_check"], "gpu_launches": main_rec["gpu_launches"],
-            "exchange": ctx.exchange_kind, "clocks": main_rec["clocks"],
+            "exchange": ctx.exchange_kind + ("; timed loops PIPELINED: each step pushes its keys and merges the previous "
+                                             "step's (results trail by one step)" if ctx.pipelined else ""),
+            "clocks": main_rec["clocks"],
+            "per_rank": main_rec.get("per_rank"),
             "other_batches": [compact(r) for r in head["batches"][1:]],
             "other_workloads": [
                 o if "error" in o else

@@ -35,6 +35,7 @@ extern "C" {
 
 #define MFAR_ABI_VERSION 1
 #define MFAR_TILE_DOCS 128   /* docs per corpus tile (UMMA M)                       */
+#define MFAR_EXCHANGE_SLOTS 4   /* key / flag slots per (rank, query) in an exchange buffer (epoch % slots) */
 #define MFAR_MAX_K 128       /* top-k depth limit (reference hard-codes k = 100)    */
 #define MFAR_MAX_FIELDS 64   /* dense + sparse fields (reference max: 44, PRIME)    */
 
@@ -224,19 +225,33 @@ MFAR_API int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k
  *   peer_buffers_host: HOST array of `world` device addresses; entry r = rank r's exchange buffer as mapped into
  *     THIS process (CUDA VMM / IPC; torch.distributed._symmetric_memory provides them), each of
  *     mfar_exchange_buffer_bytes(world, q_cap, k_cap) bytes, zero-filled once before the first call;
- *   epoch: 1, 2, 3, ... - must increase by one per call, identically on every rank;
+ *   epoch: 1, 2, 3, ... - must increase by one per call, identically on every rank (slot = epoch % MFAR_EXCHANGE_SLOTS);
  *   every rank must call with the same Q, k_in, k.  world <= 8, world * k_in <= 1024. */
 MFAR_API size_t mfar_exchange_buffer_bytes(int world, int q_cap, int k_cap);
 MFAR_API int mfar_topk_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
                              const uint64_t* peer_buffers_host, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
                              float* out_scores, int64_t* out_ids, void* stream);
-/* Same exchange with the call counter kept in DEVICE memory (int32, zero before the first call, owned by the caller):
+/* Same exchange with the call counter kept in DEVICE memory (epoch_dev: int32 [1 + MFAR_EXCHANGE_SLOTS], zero before the
+ * first call, owned by the caller: word 0 = the counter, words 1.. = the batch size each slot's epoch was pushed with):
  * the call enqueues a one-thread kernel that increments it, then the exchange kernel that reads it - no host-side value
  * is baked into the launch, so the whole sharded step (mixture weights, scoring, local merge, exchange) can be captured
  * once in a CUDA graph and replayed.  Every rank must issue the same number of calls. */
 MFAR_API int mfar_topk_exchange_merge_dev_epoch(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
                                        const uint64_t* peer_buffers_host, int q_cap, int k_cap, int32_t* epoch_dev,
                                        uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* stream);
+/* The exchange in two halves, for a PIPELINED sharded step: `push` opens a new epoch (increments *epoch_dev) and stores
+ * this rank's keys into every rank's buffer without waiting for anybody; `wait_merge(lag)` merges epoch
+ * (*epoch_dev - lag) - lag 0: the epoch just pushed (push + wait_merge(0) == mfar_topk_exchange_merge_dev_epoch),
+ * lag 1: the previous one.  A step that pushes its own keys and merges the PREVIOUS step's never waits for the slowest
+ * rank of the current step: the peers' pushes it needs landed a whole step ago.  Results then trail the inputs by one
+ * call; the first wait_merge(1) (epoch 0) returns empty lists; finish a stream of batches with wait_merge(0).
+ * k_in must not change between a push and the wait_merge that reads it; after a change of Q a lag-1 merge returns empty
+ * lists for the queries the previous epoch did not push. */
+MFAR_API int mfar_topk_exchange_push(const uint64_t* local_keys, int Q, int k_in, int rank, int world,
+                            const uint64_t* peer_buffers_host, int q_cap, int k_cap, int32_t* epoch_dev, void* stream);
+MFAR_API int mfar_topk_exchange_wait_merge(int Q, int k_in, int k, int rank, int world, const uint64_t* peer_buffers_host,
+                                  int q_cap, int k_cap, const int32_t* epoch_dev, int lag, uint64_t* out_keys,
+                                  float* out_scores, int64_t* out_ids, void* stream);
 
 /* The candidate stage of trec_eval_step (mfar/modeling/contrastive.py:676-696) for a whole batch in one launch: per
  * query the union of the per-field hit lists (678-679), the re-scoring of that union under every field (681-683,

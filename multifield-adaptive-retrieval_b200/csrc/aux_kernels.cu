@@ -396,7 +396,7 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
 
 // ---------------------------------------------------------------------------------------
 // Cross-GPU exchange + merge in ONE kernel over NVLink peer memory (replaces ncclAllGather + merge).
-// Every rank owns a buffer [flags: 2][world][q_cap] i32 | [keys: 2][world][q_cap][k_cap] u64 that all peers have
+// Every rank owns a buffer [flags: S][world][q_cap] i32 | [keys: S][world][q_cap][k_cap] u64 (S = 4 slots) that all peers have
 // mapped (CUDA VMM / torch symmetric memory).  A grid of min(Q, 296) CTAs - all co-resident (2 per SM) - walks the
 // queries b, b + grid, ... in TWO sweeps:
 //   1. PUSH   for each of its queries, the rank's local top-k keys go into slot [parity][rank][q] of EVERY rank's
@@ -406,8 +406,10 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
 // No CTA waits before it has pushed everything it owns, and every CTA of the grid is resident, so every push of every
 // rank is issued regardless of how the hardware orders CTAs: the wait always terminates once all ranks have launched
 // (round 1 used one CTA per query and relied on CTAs being scheduled in index order when Q exceeded the resident
-// capacity).  Buffers alternate by epoch parity: a peer can only be one call ahead (it needs this rank's next push to
-// finish its next call), so two slots are enough.
+// capacity).  Slots rotate with the epoch (epoch % 4).  Complete exchanges: a peer can only be one call ahead (it needs
+// this rank's next push to finish its next call).  Pipelined exchanges (push epoch e, merge epoch e-1 in the same
+// step): a peer's push of e+2 can precede this rank's merge of e-1, its push of e+3 cannot (that needs this rank's
+// push of e+1, which follows the merge of e-1 in stream order) - hence four slots.
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 constexpr int kExchangeMaxCtas = 2 * kNumSmsB200;
@@ -422,21 +424,16 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(kMergeThreads, 2)
-exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int Q, int k_in, PeerBufs peers, int rank, int world,
-                      int q_cap, int k_cap, int epoch_arg, const int* __restrict__ epoch_dev, int k,
-                      uint64_t* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-                      int* __restrict__ err) {
-  __shared__ uint64_t buf[kMergeBuf];
+constexpr int kExchangeSlots = MFAR_EXCHANGE_SLOTS;   // key / flag slots per (rank, query), indexed by epoch % slots
+
+// sweep 1: this CTA's queries -> every rank's buffer, then the flags
+__device__ __forceinline__ void exchange_push(const uint64_t* __restrict__ local_keys, int Q, int k_in,
+                                              const PeerBufs& peers, int rank, int world, int q_cap, int k_cap, int epoch) {
   const int t = threadIdx.x;
-  // the call counter: a kernel argument, or - so that the launch can be replayed from a CUDA graph - a device word
-  // that bump_epoch_kernel (same stream, just before this kernel) increments
-  const int epoch = epoch_dev ? *epoch_dev : epoch_arg;
-  const int parity = epoch & 1;
-  const size_t flag_bytes = size_t(2) * world * q_cap * sizeof(int);
-  // 1. push everything this CTA owns
+  const int sl = epoch % kExchangeSlots;
+  const size_t flag_bytes = size_t(kExchangeSlots) * world * q_cap * sizeof(int);
   for (int q = blockIdx.x; q < Q; q += gridDim.x) {
-    const size_t slot = (size_t(parity) * world + rank) * q_cap + q;          // [parity][rank][q]
+    const size_t slot = (size_t(sl) * world + rank) * q_cap + q;              // [slot][rank][q]
     for (int i = t; i < world * k_in; i += kMergeThreads) {
       const int r = i / k_in, j = i % k_in;
       uint64_t* dst = reinterpret_cast<uint64_t*>(peers.base[r] + flag_bytes) + slot * k_cap + j;
@@ -446,14 +443,29 @@ exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int Q, int k_in, 
     __syncthreads();
     if (t < world) st_release_sys(reinterpret_cast<int*>(peers.base[t]) + slot, epoch);
   }
-  // 2. wait (bounded: a peer that never arrives becomes an error, not a hang) and merge
+}
+
+// sweep 2: wait (bounded: a peer that never arrives becomes an error, not a hang) and merge the keys of `epoch`
+__device__ __forceinline__ void exchange_wait_merge(uint64_t* buf, int Q, int q_pushed, int k_in, const PeerBufs& peers, int rank,
+                                                    int world, int q_cap, int k_cap, int epoch, int k,
+                                                    uint64_t* __restrict__ out_keys, float* __restrict__ out_scores,
+                                                    int64_t* __restrict__ out_ids, int* __restrict__ err) {
+  const int t = threadIdx.x;
+  const int sl = epoch % kExchangeSlots;
+  const size_t flag_bytes = size_t(kExchangeSlots) * world * q_cap * sizeof(int);
   const uint64_t* mine = reinterpret_cast<const uint64_t*>(peers.base[rank] + flag_bytes);
   for (int q = blockIdx.x; q < Q; q += gridDim.x) {
-    if (t < world) {
-      const int* f = reinterpret_cast<const int*>(peers.base[rank]) + (size_t(parity) * world + t) * q_cap + q;
+    const bool live = epoch >= 1 && q < q_pushed;                              // else: nothing was pushed for this query
+    if (live && t < world) {
+      const int* f = reinterpret_cast<const int*>(peers.base[rank]) + (size_t(sl) * world + t) * q_cap + q;
       const unsigned long long t0 = clock64();
       while (ld_acquire_sys(f) != epoch) {
         if (clock64() - t0 > 20000000000ull) {                                // ~10 s
+#ifdef MFAR_TIMEOUT_EXIT   // debug build: say what was being waited for, then leave instead of trapping
+          printf("[mfar_b200] exchange wait timed out: rank %d waits for rank %d, query %d, epoch %d (slot %d), flag %d\n",
+                 rank, t, q, epoch, sl, ld_acquire_sys(f));
+          asm volatile("exit;");
+#endif
           atomicExch(err, 31);
           __threadfence_system();
           asm volatile("trap;");
@@ -464,9 +476,9 @@ exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int Q, int k_in, 
     __syncthreads();
     for (int i = t; i < kMergeBuf; i += kMergeThreads) {                      // all data is in this rank's own buffer now
       uint64_t key = 0ull;
-      if (i < world * k_in) {
+      if (live && i < world * k_in) {
         const int r = i / k_in, j = i % k_in;
-        key = __ldcg(mine + ((size_t(parity) * world + r) * q_cap + q) * k_cap + j);
+        key = __ldcg(mine + ((size_t(sl) * world + r) * q_cap + q) * k_cap + j);
       }
       buf[i] = key;
     }
@@ -481,7 +493,34 @@ exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int Q, int k_in, 
   }
 }
 
-__global__ void bump_epoch_kernel(int* epoch_dev) { *epoch_dev += 1; }
+// mode 0: push + wait + merge of the same epoch (one call = one complete exchange);
+// mode 1: push only;  mode 2: wait + merge of epoch - lag (the PIPELINED exchange: a step pushes its keys and merges
+// the previous step's, whose peer pushes landed a whole step ago - no rank waits for the slowest one any more)
+__global__ void __launch_bounds__(kMergeThreads, 2)
+exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int Q, int k_in, PeerBufs peers, int rank, int world,
+                      int q_cap, int k_cap, int epoch_arg, const int* __restrict__ epoch_dev, int mode, int lag, int k,
+                      uint64_t* __restrict__ out_keys, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+                      int* __restrict__ err) {
+  __shared__ uint64_t buf[kMergeBuf];
+  // the call counter: a kernel argument, or - so that the launch can be replayed from a CUDA graph - a device word
+  // that bump_epoch_kernel (same stream, in front of the push) increments
+  const int epoch = epoch_dev ? *epoch_dev : epoch_arg;
+  if (mode != 2) exchange_push(local_keys, Q, k_in, peers, rank, world, q_cap, k_cap, epoch);
+  // how many queries the epoch being merged was pushed with (recorded by bump_epoch_kernel): a pipelined merge right
+  // after a change of batch size must not wait for queries nobody pushed
+  int q_pushed = Q;
+  if (epoch_dev && mode == 2 && epoch - lag >= 1) q_pushed = min(Q, epoch_dev[1 + (epoch - lag) % kExchangeSlots]);
+  if (mode != 1)
+    exchange_wait_merge(buf, Q, q_pushed, k_in, peers, rank, world, q_cap, k_cap, epoch - lag, k, out_keys, out_scores,
+                        out_ids, err);
+}
+
+// epoch_dev: int32 [1 + slots] = the call counter, then the batch size each slot's epoch was pushed with
+__global__ void bump_epoch_kernel(int* epoch_dev, int Q) {
+  const int e = *epoch_dev + 1;
+  *epoch_dev = e;
+  epoch_dev[1 + e % kExchangeSlots] = Q;
+}
 
 __global__ void seed_gthr_kernel(unsigned long long* gthr, const unsigned long long* seed, int Q) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -630,18 +669,18 @@ int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, i
 }
 
 int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
-                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, int* epoch_dev,
-                          uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, int* epoch_dev, int mode,
+                          int lag, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st) {
   if (world < 1 || world > kMaxPeers || world * k_in > kMergeBuf || Q > q_cap || k_in > k_cap) return MFAR_ERR_SHAPE;
   PeerBufs pb{};
   for (int r = 0; r < world; ++r) pb.base[r] = peer_bases[r];
   // the error word lives at the very end of this rank's buffer
-  int* err = reinterpret_cast<int*>(pb.base[rank] + size_t(2) * world * q_cap * sizeof(int) +
-                                    size_t(2) * world * q_cap * k_cap * sizeof(uint64_t));
-  if (epoch_dev) bump_epoch_kernel<<<1, 1, 0, st>>>(epoch_dev);
+  int* err = reinterpret_cast<int*>(pb.base[rank] + size_t(kExchangeSlots) * world * q_cap * sizeof(int) +
+                                    size_t(kExchangeSlots) * world * q_cap * k_cap * sizeof(uint64_t));
+  if (epoch_dev && mode != 2) bump_epoch_kernel<<<1, 1, 0, st>>>(epoch_dev, Q);   // a push opens a new epoch
   const int ctas = Q < kExchangeMaxCtas ? Q : kExchangeMaxCtas;               // all resident: 2 x 512 threads per SM
   exchange_merge_kernel<<<ctas, kMergeThreads, 0, st>>>(local_keys, Q, k_in, pb, rank, world, q_cap, k_cap, epoch,
-                                                        epoch_dev, k, out_keys, out_scores, out_ids, err);
+                                                        epoch_dev, mode, lag, k, out_keys, out_scores, out_ids, err);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }

@@ -467,35 +467,56 @@ int mfar_topk_merge(const uint64_t* keys, int L, int Q, int k_in, int k, uint64_
 
 size_t mfar_exchange_buffer_bytes(int world, int q_cap, int k_cap) {
   if (world < 1 || world > 8 || q_cap <= 0 || k_cap <= 0) return 0;
-  return align_up(size_t(2) * world * q_cap * sizeof(int) + size_t(2) * world * q_cap * k_cap * sizeof(uint64_t) + 16, 256);
+  return align_up(size_t(MFAR_EXCHANGE_SLOTS) * world * q_cap * sizeof(int) +
+                  size_t(MFAR_EXCHANGE_SLOTS) * world * q_cap * k_cap * sizeof(uint64_t) + 16, 256);
+}
+
+static int exchange_args_ok(int Q, int k_in, int k, int rank, int world, const uint64_t* peer_buffers_host) {
+  if (!peer_buffers_host || Q <= 0 || k_in <= 0 || rank < 0 || rank >= world) return MFAR_ERR_ARG;
+  if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
+  for (int r = 0; r < world; ++r)
+    if (!peer_buffers_host[r] || peer_buffers_host[r] % 16 != 0) return MFAR_ERR_ARG;
+  return check_arch();
 }
 
 int mfar_topk_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
                              const uint64_t* peer_buffers_host, int q_cap, int k_cap, int epoch, uint64_t* out_keys,
                              float* out_scores, int64_t* out_ids, void* stream) {
-  if (!local_keys || !peer_buffers_host || Q <= 0 || k_in <= 0 || rank < 0 || rank >= world || epoch <= 0)
-    return MFAR_ERR_ARG;
-  if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
-  for (int r = 0; r < world; ++r)
-    if (!peer_buffers_host[r] || peer_buffers_host[r] % 16 != 0) return MFAR_ERR_ARG;
-  if (int rc = check_arch()) return rc;
+  if (!local_keys || epoch <= 0) return MFAR_ERR_ARG;
+  if (int rc = exchange_args_ok(Q, k_in, k, rank, world, peer_buffers_host)) return rc;
   return launch_exchange_merge(local_keys, Q, k_in, k, rank, world,
                                reinterpret_cast<const unsigned long long*>(peer_buffers_host), q_cap, k_cap, epoch,
-                               nullptr, out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+                               nullptr, 0, 0, out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
 }
 
 int mfar_topk_exchange_merge_dev_epoch(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
                                        const uint64_t* peer_buffers_host, int q_cap, int k_cap, int32_t* epoch_dev,
                                        uint64_t* out_keys, float* out_scores, int64_t* out_ids, void* stream) {
-  if (!local_keys || !peer_buffers_host || !epoch_dev || Q <= 0 || k_in <= 0 || rank < 0 || rank >= world)
-    return MFAR_ERR_ARG;
-  if (k <= 0 || k > MFAR_MAX_K) return MFAR_ERR_SHAPE;
-  for (int r = 0; r < world; ++r)
-    if (!peer_buffers_host[r] || peer_buffers_host[r] % 16 != 0) return MFAR_ERR_ARG;
-  if (int rc = check_arch()) return rc;
+  if (!local_keys || !epoch_dev) return MFAR_ERR_ARG;
+  if (int rc = exchange_args_ok(Q, k_in, k, rank, world, peer_buffers_host)) return rc;
   return launch_exchange_merge(local_keys, Q, k_in, k, rank, world,
                                reinterpret_cast<const unsigned long long*>(peer_buffers_host), q_cap, k_cap, 0,
-                               epoch_dev, out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+                               epoch_dev, 0, 0, out_keys, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+}
+
+int mfar_topk_exchange_push(const uint64_t* local_keys, int Q, int k_in, int rank, int world,
+                            const uint64_t* peer_buffers_host, int q_cap, int k_cap, int32_t* epoch_dev, void* stream) {
+  if (!local_keys || !epoch_dev) return MFAR_ERR_ARG;
+  if (int rc = exchange_args_ok(Q, k_in, 1, rank, world, peer_buffers_host)) return rc;
+  return launch_exchange_merge(local_keys, Q, k_in, 1, rank, world,
+                               reinterpret_cast<const unsigned long long*>(peer_buffers_host), q_cap, k_cap, 0,
+                               epoch_dev, 1, 0, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int mfar_topk_exchange_wait_merge(int Q, int k_in, int k, int rank, int world, const uint64_t* peer_buffers_host,
+                                  int q_cap, int k_cap, const int32_t* epoch_dev, int lag, uint64_t* out_keys,
+                                  float* out_scores, int64_t* out_ids, void* stream) {
+  if (!epoch_dev || lag < 0 || lag > MFAR_EXCHANGE_SLOTS - 3) return MFAR_ERR_ARG;
+  if (int rc = exchange_args_ok(Q, k_in, k, rank, world, peer_buffers_host)) return rc;
+  return launch_exchange_merge(nullptr, Q, k_in, k, rank, world,
+                               reinterpret_cast<const unsigned long long*>(peer_buffers_host), q_cap, k_cap, 0,
+                               const_cast<int32_t*>(epoch_dev), 2, lag, out_keys, out_scores, out_ids,
+                               static_cast<cudaStream_t>(stream));
 }
 
 int mfar_topk_apply_zero_init(float* scores, int64_t* ids, int Q, int k, void* stream) {

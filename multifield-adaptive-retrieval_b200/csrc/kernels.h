@@ -57,8 +57,8 @@ int launch_union_rescore(const void* corpus, int64_t n_docs, int corpus_fields, 
                          int n_sparse, const int64_t* cand, int L, int k_in, int k_out, float* out_scores,
                          int64_t* out_rows, int* out_union, cudaStream_t st);
 int launch_exchange_merge(const uint64_t* local_keys, int Q, int k_in, int k, int rank, int world,
-                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, int* epoch_dev,
-                          uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
+                          const unsigned long long* peer_bases, int q_cap, int k_cap, int epoch, int* epoch_dev, int mode,
+                          int lag, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
 
 // Training-time scorer (train.cu).  Doc n = (p, s), p = n / inner, s = n % inner, row of field f at
 // docs + p*stride_p + f*stride_f + s*stride_s (elements).

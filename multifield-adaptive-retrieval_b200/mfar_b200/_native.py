@@ -40,6 +40,8 @@ PROTOTYPES = {
     "mfar_exchange_buffer_bytes": (_sz, [_i, _i, _i]),
     "mfar_topk_exchange_merge": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mfar_topk_exchange_merge_dev_epoch": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "mfar_topk_exchange_push": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "mfar_topk_exchange_wait_merge": (_i, [_i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "mfar_union_rescore": (_i, [_vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _i64, _vp, _i, _i, _i, _vp, _vp, _vp,
                                 _vp]),
     "mfar_topk_apply_zero_init": (_i, [_vp, _vp, _i, _i, _vp]),

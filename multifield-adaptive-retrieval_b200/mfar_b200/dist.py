@@ -87,6 +87,7 @@ class PeerExchange:
     def __init__(self, q_cap: int, k_cap: int = 128, group=None, device=None, peer_buffers=None, rank=None, world=None):
         self.q_cap, self.k_cap = int(q_cap), int(k_cap)
         self.epoch = 0
+        self._last_shape = None           # (Q, k_in) of the last push
         if peer_buffers is not None:                      # explicit buffers (tests: "virtual ranks" on one device)
             self.rank, self.world = int(rank), int(world)
             self._bufs = peer_buffers
@@ -108,7 +109,7 @@ class PeerExchange:
         # the call counter lives on the device and is incremented by a one-thread kernel in front of every exchange, so a
         # merge call is identical from launch to launch and can be replayed from a CUDA graph
         dev = peer_buffers[self.rank].device if peer_buffers is not None else self._bufs[0].device
-        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.epoch_dev = torch.zeros(1 + 4, dtype=torch.int32, device=dev)   # counter + batch size per exchange slot
 
     @staticmethod
     def buffer_bytes(world: int, q_cap: int, k_cap: int = 128) -> int:
@@ -122,6 +123,7 @@ class PeerExchange:
         if Q > self.q_cap or k_in > self.k_cap:
             raise ValueError(f"exchange buffers sized for [{self.q_cap},{self.k_cap}], got [{Q},{k_in}]")
         self.epoch += 1                                   # bookkeeping only (calls issued or captured so far)
+        self._last_shape = (Q, k_in)
         scores = torch.empty((Q, k), dtype=torch.float32, device=keys.device)
         ids = torch.empty((Q, k), dtype=torch.int64, device=keys.device)
         nv.check(nv.lib().mfar_topk_exchange_merge_dev_epoch(
@@ -130,14 +132,48 @@ class PeerExchange:
         return scores, ids
 
 
+    # ---- the exchange in two halves (pipelined sharded step)
+    def push(self, keys: torch.Tensor) -> None:
+        """Open a new epoch and store this rank's packed keys [Q,k_in] into every rank's buffer; waits for nobody."""
+        import ctypes
+        nv.require_device(keys, "keys")
+        Q, k_in = keys.shape
+        if Q > self.q_cap or k_in > self.k_cap:
+            raise ValueError(f"exchange buffers sized for [{self.q_cap},{self.k_cap}], got [{Q},{k_in}]")
+        self.epoch += 1
+        self._last_shape = (Q, k_in)
+        nv.check(nv.lib().mfar_topk_exchange_push(nv.ptr(keys.contiguous()), Q, k_in, self.rank, self.world,
+                                                  ctypes.addressof(self._ptr_arr), self.q_cap, self.k_cap,
+                                                  nv.ptr(self.epoch_dev), nv.stream()), "topk_exchange_push")
+
+    def wait_merge(self, k: int, lag: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Merge the keys all ranks pushed ``lag`` epochs ago (0: the epoch just pushed, 1: the one before - its peer
+        pushes landed a whole step ago, so nothing waits).  Epoch 0 (nothing pushed yet) gives (-inf, -1) rows."""
+        import ctypes
+        Q, k_in = self._last_shape
+        dev = self.epoch_dev.device
+        scores = torch.empty((Q, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((Q, k), dtype=torch.int64, device=dev)
+        nv.check(nv.lib().mfar_topk_exchange_wait_merge(Q, k_in, k, self.rank, self.world,
+                                                        ctypes.addressof(self._ptr_arr), self.q_cap, self.k_cap,
+                                                        nv.ptr(self.epoch_dev), int(lag), 0, nv.ptr(scores), nv.ptr(ids),
+                                                        nv.stream()), "topk_exchange_wait_merge")
+        return scores, ids
+
+
 class ShardedRetriever:
     """One process per GPU; wraps the rank-local ``MultiFieldRetriever`` (built over this rank's doc
     range with ``doc_id_base = shard_range(...)[0]``)."""
 
-    def __init__(self, local, group=None, exchange: Optional[PeerExchange] = None):
+    def __init__(self, local, group=None, exchange: Optional[PeerExchange] = None, pipelined: bool = False):
+        """``pipelined`` (needs ``exchange``): every ``search`` pushes its own keys and returns the merged result of
+        the PREVIOUS call (the first call returns (-inf, -1) rows); ``flush()`` returns the last batch's result.  No
+        rank then waits for the slowest rank of the current step - throughput mode for a stream of batches."""
         self.local = local
         self.group = group
         self.exchange = exchange          # None: NCCL/gloo all-gather + merge kernel; else the fused NVLink kernel
+        self.pipelined = bool(pipelined) and exchange is not None
+        self._k = None
 
     @torch.no_grad()
     def search(self, q_vecs, q_emb=None, sparse_local=None, top_k: Optional[int] = None, sparse_tokens=None):
@@ -151,6 +187,16 @@ class ShardedRetriever:
             keys = torch.nn.functional.pad(keys, (0, k - k_local))
         if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return merge_keys(keys.unsqueeze(0), k)
+        if self.pipelined:
+            self._k = k
+            self.exchange.push(keys)
+            return self.exchange.wait_merge(k, lag=1)
         if self.exchange is not None:
             return self.exchange.merge(keys, k)
         return merge_keys(all_gather_keys(keys, self.group), k)
+
+    def flush(self):
+        """Pipelined mode: the merged result of the last ``search`` call."""
+        if not self.pipelined or self._k is None:
+            raise RuntimeError("flush() belongs to a pipelined ShardedRetriever after at least one search")
+        return self.exchange.wait_merge(self._k, lag=0)

@@ -649,7 +649,8 @@ class GraphedSearch:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.scores, self.ids = self._run()
-        self.launches = r.last_launches + 1 + (2 if sharded is not None else 0)   # + mixture weights (+ epoch bump, exchange)
+        # + mixture weights (+ epoch bump, exchange; pipelined: bump, push, wait+merge of the previous batch)
+        self.launches = r.last_launches + 1 + (0 if sharded is None else (3 if getattr(sharded, "pipelined", False) else 2))
 
     def _run(self):
         if self.sharded is not None:

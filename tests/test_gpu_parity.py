@@ -485,6 +485,47 @@ def test_peer_exchange_merge_virtual_ranks():
             assert torch.equal(s_r, want_s) and torch.equal(i_r, want_i)
 
 
+def test_pipelined_exchange_virtual_ranks():
+    """push / wait_merge(lag): a step pushes its keys and merges the PREVIOUS step's (four rotating slots).  R virtual
+    ranks on one device, 7 epochs incl. changes of the batch size: every wait_merge(1) returns the merge of the previous
+    epoch's lists (empty rows for queries the previous epoch did not push, (-inf, -1) rows at the very first call),
+    wait_merge(0) at the end the last epoch's - all equal to mfar_topk_merge of the same lists."""
+    from mfar_b200.dist import PeerExchange, encode_keys, merge_keys
+    R, k = 4, 100
+    n = PeerExchange.buffer_bytes(R, 16, 128)
+    bufs = [torch.zeros(n, dtype=torch.uint8, device=DEV) for _ in range(R)]
+    ex = [PeerExchange(16, 128, peer_buffers=bufs, rank=r, world=R) for r in range(R)]
+    streams = [torch.cuda.Stream() for _ in range(R)]
+    g = np.random.RandomState(9)
+    want_prev = None
+    for Q in (11, 11, 5, 5, 11, 11, 11):
+        scores = g.standard_normal((R, Q, k)).astype(np.float32) * 10
+        ids = np.stack([g.permutation(100000)[: Q * k].reshape(Q, k) + 100000 * r for r in range(R)])
+        keys = torch.from_numpy(encode_keys(scores, ids).view(np.int64)).to(DEV)         # [R,Q,k]
+        want = merge_keys(keys, k)
+        torch.cuda.synchronize()
+        outs = []
+        for r in range(R):
+            with torch.cuda.stream(streams[r]):
+                ex[r].push(keys[r])
+                outs.append(ex[r].wait_merge(k, lag=1))
+        torch.cuda.synchronize()
+        for s_r, i_r in outs:
+            assert s_r.shape == (Q, k)
+            n_prev = 0 if want_prev is None else min(Q, want_prev[0].shape[0])
+            assert torch.equal(s_r[:n_prev], want_prev[0][:n_prev]) if n_prev else True
+            assert torch.equal(i_r[:n_prev], want_prev[1][:n_prev]) if n_prev else True
+            assert torch.isinf(s_r[n_prev:]).all() and (i_r[n_prev:] == -1).all()
+        want_prev = want
+    outs = []
+    for r in range(R):
+        with torch.cuda.stream(streams[r]):
+            outs.append(ex[r].wait_merge(k, lag=0))
+    torch.cuda.synchronize()
+    for s_r, i_r in outs:
+        assert torch.equal(s_r, want_prev[0]) and torch.equal(i_r, want_prev[1])
+
+
 def test_topk_edge_cases():
     fields, q, _, W = synth(51, 300, 64, 2, 0, 2, False)
     r = build(fields, W, False, 0, 100)
