@@ -226,7 +226,7 @@ class Ctx:
         self.dist.all_reduce(t)
         return t.tolist()
 
-    def calibrate(self, n_dense, Q, shard_docs, seconds=1.0):
+    def calibrate(self, n_dense, Q, shard_docs, seconds=1.5):
         """Speed-weighted shards: the job runs at the pace of its slowest rank, and the GPUs of a node settle at different
         clocks under the 1 kW cap (a few per cent apart).  Each rank times the scoring kernel on an identical calibration
         shard of the REAL shard size (so the kernel is in the same power-capped regime as in the run; capped at 2.5M docs)
