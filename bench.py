@@ -18,6 +18,7 @@ import argparse
 import ctypes
 import gc
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -625,10 +626,16 @@ def run_workload(ctx: Ctx, name, batches, steps, warmup, headline=False):
            "shard_docs": wl.hi - wl.lo, "cuda_graph": graph, "setup_s": wl.setup_s, "batches": []}
     for bi, Q in enumerate(batches):
         main = headline and bi == 0
-        st = steps if main else max(5, steps // 2)
+        st, wu = (steps, warmup) if main else (max(5, steps // 2), 3)
         pool = wl.make_batches(Q, 4 if main else 2)
-        ms, launches, km, clocks = wl.time_device(pool, st, warmup if main else 3, graph, profile=True,
-                                                  sample_clocks=main)
+        if not main:
+            # Side legs with sub-millisecond steps: ten steps after three warm-ups are ~10 ms in whatever clock / power
+            # state the previous leg left behind (seen: the same PRIME-shaped kernel at 0.88 ms right after the 1 kW
+            # headline leg, 0.63 ms on its own).  Size them by TIME instead: >= 40 ms of warm-up, >= 100 ms timed.
+            est = wl.time_device(pool, 3, 2, graph, profile=False)[0] / 3
+            st = max(st, min(300, int(math.ceil(100.0 / max(est, 1e-3)))))
+            wu = max(wu, min(100, int(math.ceil(40.0 / max(est, 1e-3)))))
+        ms, launches, km, clocks = wl.time_device(pool, st, wu, graph, profile=True, sample_clocks=main)
         k_ms = statistics.mean(km) if km else None
         rec = {"batch": Q, "value": Q * st / (ms * 1e-3), "ms_per_step": ms / st, "steps": st,
                "roofline": wl.roofline(Q, k_ms, len(km), ms, st), "gpu_launches": launches}

@@ -273,16 +273,25 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int epi_warp = warp - 2;
     float acc[QP];
     int u = 0;
+    // Query c's list, thresholds and counter are looked after by warp c % 4, one query per LANE: cq = this lane's query.
+    const int cq = epi_warp + (kEpiThreads / 32) * lane;
+    const bool cq_live = lane < QP / (kEpiThreads / 32) && cq < nq;
+    if (cq_live) {                                   // the seed (capi.cu, threshold seeding), if any
+      const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + q0 + cq);
+      if (gt > s_thr[cq]) { s_thr[cq] = gt; s_thrf[cq] = key_score(gt); }
+    }
+    epi_bar_sync();
     for (int i = 0; i < my_tiles; ++i) {
       const int t = g + i * gridDim.x;
-      {                                              // adopt the best threshold any CTA found for these queries
-        const int et0 = threadIdx.x - 64;
-        if (et0 < nq) {
-          const unsigned long long gt = ld_relaxed_u64(p.ws.gthr + q0 + et0);   // incl. the pooled bound, common.cuh
-          if (gt > s_thr[et0]) { s_thr[et0] = gt; s_thrf[et0] = key_score(gt); }
-        }
-        epi_bar_sync();
-      }
+      // the best threshold any CTA found for this lane's query (incl. the pooled bound, common.cuh): the load is issued
+      // here and consumed after the tile's pushes, so its L2 round trip hides behind the accumulation (it used to sit,
+      // with a block barrier, at the head of every tile - ~10 % of a single-field tile)
+      unsigned long long gt_next = 0ull;
+      if (cq_live) gt_next = ld_relaxed_u64(p.ws.gthr + q0 + cq);
+      // Long tiles / few tiles per CTA (PRIME-shaped: 7 tiles of 22 fields): one tile of staleness costs a whole extra
+      // round of compactions, so the value is applied BEFORE this tile's pushes (one more block barrier, nothing next
+      // to a 100 us tile); short tiles apply it after the pushes, for the next tile.
+      const bool adopt_before_push = p.n_dense >= 8 || my_tiles <= 32;
       // The accumulators start from the pre-mixed sparse term: its QP loads per doc (coalesced across the warp's
       // 32 docs) are issued here, ahead of the wait for the tile's first accumulator, instead of serialising with
       // the push loop after the last field.
@@ -324,6 +333,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         mbar_arrive(&tempty_bar[buf]);             // 128 arrivals free the accumulator buffer
       }
       // ---- tile done: filter, push
+      if (adopt_before_push) {
+        if (cq_live && gt_next > s_thr[cq]) { s_thr[cq] = gt_next; s_thrf[cq] = key_score(gt_next); }
+        epi_bar_sync();
+      }
       if (doc_local < p.n_docs) {
         const uint32_t doc_id = uint32_t(p.doc_id_base + doc_local);
         // Float pre-filter per GROUP of 8 queries: max_j(score[c0+j] - score of query c0+j's threshold) >= 0 decides
@@ -351,24 +364,29 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
       epi_bar_sync();
-      for (int c = epi_warp; c < nq; c += kEpiThreads / 32) {
+      // lists that could overflow during the next tile, found lane-parallel (a serial walk over the warp's 16 queries
+      // with a shared-memory load and a branch each was ~20 % of a single-field tile's epilogue)
+      unsigned need = __ballot_sync(0xffffffffu, cq_live && s_cnt[cq] > kCandCap - kTileDocs);
+      if (!adopt_before_push && cq_live && gt_next > s_thr[cq]) { s_thr[cq] = gt_next; s_thrf[cq] = key_score(gt_next); }
+      __syncwarp();
+      while (need) {
+        const int c = epi_warp + (kEpiThreads / 32) * (__ffs(need) - 1);
+        need &= need - 1u;
         const int cnt = s_cnt[c];
-        if (cnt > kCandCap - kTileDocs) {
-          uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
-          int cnt_new = p.k;                           // every round: warp select (see score_qs.cu)
-          const int r = pooled_rank(p.k, int(gridDim.x));
-          uint64_t bound_r = 0ull;
-          const uint64_t kth = warp_select_list(list, cnt, p.k, kCandCap - kTileDocs, lane, &cnt_new, r, &bound_r);
-          __syncwarp();
-          const unsigned long long pooled = pool_publish_and_min(p.ws.pool, int(gridDim.x), p.ws.q_pad, g, q0 + c,
-                                                                 bound_r, lane);
-          if (lane == 0) {
-            if (kth > s_thr[c]) s_thr[c] = kth;
-            if (pooled > s_thr[c]) s_thr[c] = pooled;
-            s_thrf[c] = key_score(s_thr[c]);
-            s_cnt[c] = cnt_new;
-            atomicMax(p.ws.gthr + q0 + c, s_thr[c]);
-          }
+        uint64_t* list = p.ws.cand_keys + (int64_t(g) * p.ws.q_pad + q0 + c) * kCandCap;
+        int cnt_new = p.k;                             // every round: warp select (see score_qs.cu)
+        const int r = pooled_rank(p.k, int(gridDim.x));
+        uint64_t bound_r = 0ull;
+        const uint64_t kth = warp_select_list(list, cnt, p.k, kCandCap - kTileDocs, lane, &cnt_new, r, &bound_r);
+        __syncwarp();
+        const unsigned long long pooled = pool_publish_and_min(p.ws.pool, int(gridDim.x), p.ws.q_pad, g, q0 + c,
+                                                               bound_r, lane);
+        if (lane == 0) {
+          if (kth > s_thr[c]) s_thr[c] = kth;
+          if (pooled > s_thr[c]) s_thr[c] = pooled;
+          s_thrf[c] = key_score(s_thr[c]);
+          s_cnt[c] = cnt_new;
+          atomicMax(p.ws.gthr + q0 + c, s_thr[c]);
         }
       }
       epi_bar_sync();

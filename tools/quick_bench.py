@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--sparse-fields", type=int, default=-1, help="override the workload's sparse field count")
+    ap.add_argument("--dense-fields", type=int, default=-1, help="override the workload's dense field count")
     args = ap.parse_args()
     from mfar_b200 import _native as nv
     from mfar_b200 import synth
@@ -36,6 +38,8 @@ def main():
     from mfar_b200.modeling.weighting import LinearWeights
     n, Fd, Fs = synth.SHAPES[args.workload]
     n = args.docs or n
+    Fs = Fs if args.sparse_fields < 0 else args.sparse_fields
+    Fd = Fd if args.dense_fields < 0 else args.dense_fields
     dev = torch.device("cuda", 0)
     pc = None
     if Fd:
