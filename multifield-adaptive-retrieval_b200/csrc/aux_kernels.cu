@@ -278,7 +278,8 @@ __device__ __forceinline__ void merge_sweep(const uint64_t* __restrict__ keys, c
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, const uint64_t* __restrict__ thr,
              int L, int q_stride, int slots, int k, int sc_cap, uint64_t* __restrict__ out_keys,
-             float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+             float* __restrict__ out_scores, int64_t* __restrict__ out_ids, const uint64_t* __restrict__ extra,
+             int extra_n) {
   extern __shared__ uint32_t sc[];                     // [sc_cap] score words of the candidates
   __shared__ uint64_t buf[kMergeBuf];
   __shared__ int s_cnt, s_probe;
@@ -301,14 +302,19 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
   {
     const unsigned long long thr0 = s_thr;
     unsigned int mx = 0u;
-    merge_sweep(keys, counts, L, q_stride, slots, q, [&](uint64_t key) {
+    auto take = [&](uint64_t key) {
       if (key >= thr0) {
         const int pos = atomicAdd(&s_cnt, 1);
         const uint32_t w = uint32_t(key >> 32);
         if (pos < sc_cap) sc[pos] = w;
         mx = w > mx ? w : mx;
       }
-    });
+    };
+    merge_sweep(keys, counts, L, q_stride, slots, q, take);
+    for (int j = t; j < extra_n; j += kMergeThreads) {   // the extra list (e.g. the top k of a prefix scored earlier)
+      const uint64_t key = extra[int64_t(q) * extra_n + j];
+      if (key != 0ull) take(key);
+    }
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((t & 31) == 0 && mx) atomicMax(&s_max, mx);
   }
@@ -338,9 +344,14 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
       if (t == 0) s_cnt = 0;
       __syncthreads();
       const unsigned long long thr0 = s_thr;
-      merge_sweep(keys, counts, L, q_stride, slots, q, [&](uint64_t key) {
+      auto gather = [&](uint64_t key) {
         if (key >= thr0 && uint32_t(key >> 32) >= lo) buf[atomicAdd(&s_cnt, 1)] = key;
-      });
+      };
+      merge_sweep(keys, counts, L, q_stride, slots, q, gather);
+      for (int j = t; j < extra_n; j += kMergeThreads) {
+        const uint64_t key = extra[int64_t(q) * extra_n + j];
+        if (key != 0ull) gather(key);
+      }
       __syncthreads();
       const int cc = s_cnt;
       const int n = pow2_at_least(cc > k ? cc : k, 128);
@@ -360,7 +371,7 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
   __syncthreads();
   // ---- streaming path
   const int total = L * slots;
-  for (int base = 0; base < total; base += kMergeThreads) {
+  for (int base = 0; base < total + extra_n; base += kMergeThreads) {
     const int i = base + t;
     if (i < total) {
       const int l = i / slots, sl = i % slots;
@@ -369,6 +380,9 @@ merge_kernel(const uint64_t* __restrict__ keys, const int* __restrict__ counts, 
         const uint64_t key = keys[(int64_t(l) * q_stride + q) * slots + sl];
         if (key != 0ull && key >= s_thr) buf[atomicAdd(&s_cnt, 1)] = key;
       }
+    } else if (i < total + extra_n) {
+      const uint64_t key = extra[int64_t(q) * extra_n + (i - total)];
+      if (key != 0ull && key >= s_thr) buf[atomicAdd(&s_cnt, 1)] = key;
     }
     __syncthreads();
     const int cs = s_cnt;                              // snapshot, then barrier: the branch below must be
@@ -652,10 +666,12 @@ int launch_sparse_premix_coo(const int32_t* keys, const void* vals, int val_dtyp
 }
 
 int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
-                 int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st) {
+                 int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st, const uint64_t* extra,
+                 int extra_n) {
   if (int64_t(L) * slots > (int64_t(1) << 30)) return MFAR_ERR_SHAPE;
+  if (extra == nullptr) extra_n = 0;
   // score-word scratch: every slot of every list if that fits ~150 KB, else a cap (overflow -> streaming path)
-  int sc_cap = int(std::min<int64_t>(int64_t(L) * slots, 38 * 1024));
+  int sc_cap = int(std::min<int64_t>(int64_t(L) * slots + extra_n, 38 * 1024));
   sc_cap = (sc_cap + 3) & ~3;
   const size_t smem = size_t(sc_cap) * sizeof(uint32_t);
   static PerDeviceOnce attr_once;
@@ -663,7 +679,7 @@ int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, i
     return cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   }));
   merge_kernel<<<Q, kMergeThreads, smem, st>>>(keys, counts, thr, L, q_stride, slots, k, sc_cap, out_keys, out_scores,
-                                              out_ids);
+                                              out_ids, extra, extra_n);
   MFAR_CUDA_OK(cudaGetLastError());
   return MFAR_OK;
 }

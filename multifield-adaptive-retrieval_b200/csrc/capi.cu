@@ -293,6 +293,7 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   // Not for small batches: below ~32 queries there are few lists to compact and the prefix's fixed ~0.1 ms shows
   // (measured: MAG-shaped Q=64 step 1.04 -> 0.93 ms, Q=512 2.82 -> 2.74 ms, 1.25M-doc shard Q=512 6.92 -> 6.60 ms,
   // single_ Q=128 3.21 -> 2.73 ms; Q=1 0.81 -> 0.87 ms without this rule).
+  const uint64_t* prefix_keys = nullptr;              // set when a scored prefix is left out of the main pass
   const bool seed = n_dense > 0 && (g.impl == MFAR_IMPL_TCGEN05 || g.impl == MFAR_IMPL_TCGEN05_QS) && Q >= 32 &&
                     a.n_tiles >= 16 * g.workers && ws_seed > 0;
   if (seed) {
@@ -314,6 +315,19 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
     if ((rc = launch_seed_from_keys(pref_keys, Q, k, seed_thr, st))) return rc;
     a.gthr_seed = seed_thr;
     t_last_launches += 4;                             // prefix scoring + merge + seed, and the copy into the main pass
+    // The prefix is not scored twice: the main pass starts behind it (every per-doc pointer advanced by the prefix's
+    // whole tiles) and the final merge takes the prefix's ranked top k as one more list.
+    const int64_t skip = ap.n_docs;
+    a.corpus = static_cast<const char*>(a.corpus) + size_t(g.workers) * a.corpus_fields * kTileDocs * a.dim * 2;
+    a.n_tiles -= g.workers;
+    a.n_docs -= skip;
+    a.doc_id_base += skip;
+    if (a.base) a.base += skip;
+    if (a.sparse) {
+      a.sparse = static_cast<const char*>(a.sparse) + size_t(skip) * (a.sparse_dtype == MFAR_F16 ? 2 : 4);
+      a.sparse_cols = a.sparse_ld - skip;
+    }
+    prefix_keys = pref_keys;
   }
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][0], st));
@@ -331,7 +345,7 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   if (g.impl == kImplRows && n_docs >= 4096) ++t_last_launches;   // + the threshold-seed kernel
   TopkWorkspace ws = carve_workspace(workspace, g.lists, g.q_pad_total);
   rc = launch_merge(ws.cand_keys, ws.cand_cnt, ws.cand_thr, g.lists, g.q_pad_total, kCandCap, Q, k, out_keys,
-                    out_scores, out_ids, st);
+                    out_scores, out_ids, st, prefix_keys, prefix_keys ? k : 0);
   if (rc) return rc;
   ++t_last_launches;
   return MFAR_OK;

@@ -48,8 +48,10 @@ int launch_sparse_premix(const void* sparse, int sparse_dtype, int64_t sparse_ld
 int launch_sparse_premix_coo(const int32_t* keys, const void* vals, int val_dtype, const int64_t* field_offsets_host,
                              int n_sparse, const float* w, int w_ld, int w_off, int Q, int64_t doc_id_base,
                              int64_t n_docs, float* base, int64_t base_ld, cudaStream_t st);
+// extra / extra_n: one more list per query, [Q, extra_n] keys (0 = empty slot), or nullptr
 int launch_merge(const uint64_t* keys, const int* counts, const uint64_t* thr, int L, int q_stride, int slots, int Q,
-                 int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st);
+                 int k, uint64_t* out_keys, float* out_scores, int64_t* out_ids, cudaStream_t st,
+                 const uint64_t* extra = nullptr, int extra_n = 0);
 int launch_zero_init(float* scores, int64_t* ids, int n, cudaStream_t st);
 // union of per-field candidate lists + gather-rescore + mixture + top-k for a whole batch (union_rescore.cu)
 int launch_union_rescore(const void* corpus, int64_t n_docs, int corpus_fields, int n_dense, int dim, const void* q_vecs,
@@ -92,6 +94,8 @@ struct ScoreArgs {
   const void* sparse;
   int sparse_dtype;         // MFAR_F16 / MFAR_F32
   int64_t sparse_ld;
+  int64_t sparse_cols;      // valid columns of a row counted from `sparse` (0 = sparse_ld; smaller when the pointer has been
+                            // advanced past a scored prefix, capi.cu)
   int n_sparse;
   int64_t doc_id_base;
   int k;

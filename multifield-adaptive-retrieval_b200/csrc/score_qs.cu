@@ -662,7 +662,8 @@ static int launch_qs_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   CUtensorMap map_sp = map_b;                       // unused by the dense-only kernels
   if (SP) {
     rc = make_tensor_map_sparse_rows(&map_sp, a.sparse, a.sparse_dtype == MFAR_F16, uint64_t(a.sparse_ld),
-                                     uint32_t(a.n_sparse), uint64_t(a.Q), kQsQ);
+                                     uint64_t(a.sparse_cols ? a.sparse_cols : a.sparse_ld), uint32_t(a.n_sparse),
+                                     uint64_t(a.Q), kQsQ);
     if (rc) return rc;
   }
   static PerDeviceOnce attr_once;   // per template instantiation

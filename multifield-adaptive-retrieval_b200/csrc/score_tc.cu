@@ -42,6 +42,7 @@ struct TcParams {
   int64_t base_ld;
   const void* sparse;   // [Q, n_sparse, sparse_ld] f16/f32 gathered by the epilogue (exclusive with base), rows 32-B aligned
   int64_t sparse_ld;
+  int64_t sparse_cols;  // columns addressable from `sparse` (<= sparse_ld)
   int n_sparse;
   int sparse_f16;
   int64_t doc_id_base;
@@ -81,7 +82,7 @@ __device__ __forceinline__ void tc_stage_sparse(float* base_s, const TcParams& p
       const int pid = (b0 + i) * kStagerThreads + et;
       cq[i] = pid / kGroups; gq[i] = pid % kGroups;
       const int64_t d = tile_doc0 + gq[i] * kLoadDocs;
-      live[i] = cq[i] < nq && d < p.sparse_ld;
+      live[i] = cq[i] < nq && d < p.sparse_cols;
       src[i] = static_cast<const char*>(p.sparse) + (int64_t(q0 + cq[i]) * p.n_sparse * p.sparse_ld + d) * kEs;
     }
     float acc[kBatch][kLoadDocs];
@@ -434,6 +435,7 @@ static int launch_tc_impl(const ScoreArgs& a, void* ws_base, int workers, int q_
   p.n_dense = a.n_dense; p.k_chunks = a.dim / kChunkK; p.Q = a.Q; p.w = a.w; p.w_ld = a.w_ld; p.base = a.base;
   p.base_ld = a.base_ld; p.doc_id_base = a.doc_id_base; p.k = a.k;
   p.sparse = a.sparse; p.sparse_ld = a.sparse_ld; p.n_sparse = a.sparse ? a.n_sparse : 0;
+  p.sparse_cols = a.sparse_cols ? a.sparse_cols : a.sparse_ld;
   p.sparse_f16 = a.sparse_dtype == MFAR_F16;
   if (a.sparse && (a.base || !sparse_rows_fusable(a.sparse, a.sparse_dtype, a.sparse_ld))) return MFAR_ERR_ARG;
   const int n_w = a.n_dense + p.n_sparse;

@@ -310,12 +310,13 @@ static inline int make_tensor_map_kchunked(CUtensorMap* map, const void* base, u
 // 3-D view of a [Q, n_sparse, ld] f16/f32 score tensor: dims (ld | n_sparse | Q), box = (128 bytes of docs, 1 field,
 // box_q queries), 128-byte swizzled: the rows of one field for a tile of queries, one row per 128-byte line.
 // Out-of-range docs / queries are zero-filled by the TMA unit.  Needs a 16-byte aligned base and row pitch.
-static inline int make_tensor_map_sparse_rows(CUtensorMap* map, const void* base, bool f16, uint64_t ld,
+// ld: row pitch in elements; cols <= ld: columns addressable from `base` (reads past them are zero-filled)
+static inline int make_tensor_map_sparse_rows(CUtensorMap* map, const void* base, bool f16, uint64_t ld, uint64_t cols,
                                               uint32_t n_sparse, uint64_t Q, uint32_t box_q) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return MFAR_ERR_CUDA;
   const uint64_t es = f16 ? 2 : 4;
-  cuuint64_t gdim[3] = {ld, n_sparse, Q};
+  cuuint64_t gdim[3] = {cols, n_sparse, Q};
   cuuint64_t gstride[2] = {ld * es, ld * es * n_sparse};
   cuuint32_t box[3] = {cuuint32_t(128 / es), 1, box_q};
   cuuint32_t estr[3] = {1, 1, 1};
