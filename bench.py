@@ -294,8 +294,7 @@ class Workload:
 
     def __init__(self, ctx: Ctx, name: str, docs_override: int = 0):
         from mfar_b200 import synth
-        from mfar_b200.dist import ShardedRetriever, weighted_shard_ranges
-        from mfar_b200.modeling.retrieval import MultiFieldRetriever
+        from mfar_b200.dist import ShardedRetriever, held_ranges, weighted_shard_ranges
         from mfar_b200.modeling.weighting import LinearWeights
         self.ctx, self.name = ctx, name
         a = ctx.args
@@ -303,12 +302,24 @@ class Workload:
         if docs_override:
             self.n_total = docs_override
         self.bm25_mode = a.sparse_mode == "bm25" and self.n_sparse > 0
-        self.lo, self.hi = weighted_shard_ranges(self.n_total, ctx.weights)[ctx.rank]
+        ranges = weighted_shard_ranges(self.n_total, ctx.weights)
+        self.cuts = self.base_cuts = [r[0] for r in ranges] + [self.n_total]
+        self.lo, self.hi = ranges[ctx.rank]
+        # Tunable boundaries (dense-only scorers at N > 1, --balance auto): every rank keeps a margin of its neighbours'
+        # docs resident, so the boundaries can follow the measured per-rank step time (tune_boundaries) by pointer offset.
+        self.margin = 0
+        if ctx.world > 1 and a.balance == "auto" and self.n_dense and not self.n_sparse:
+            self.margin = -(-int(0.06 * self.n_total / ctx.world) // 128) * 128
+        self.held_lo, self.held_hi = held_ranges(self.cuts, self.margin, self.n_total)[ctx.rank]
+        self.tuning = None
         t0 = time.perf_counter()
         if self.n_dense:
-            self.pc, self.mu = build_shard(self.n_total, self.n_dense, self.lo, self.hi, a.seed, ctx.device)
+            self.pc_held, self.mu = build_shard(self.n_total, self.n_dense, self.held_lo, self.held_hi, a.seed,
+                                                ctx.device)
+            self.pc = self.pc_held if not self.margin else self.pc_held.window(self.lo - self.held_lo, self.hi - self.lo)
         else:                                             # sparse-only scorer: nothing to pack
-            self.pc, self.mu = None, synth.corpus_mean(DIM, a.seed, ctx.device)
+            self.pc_held = self.pc = None
+            self.mu = synth.corpus_mean(DIM, a.seed, ctx.device)
         F = self.n_dense + self.n_sparse
         layer = LinearWeights(DIM, F, query_cond=True)
         with torch.no_grad():
@@ -319,6 +330,15 @@ class Workload:
             self.bm25_fields = [synth.make_bm25_field(self.n_total, a.seed + 300 + j, ctx.device,
                                                       doc_range=(self.lo, self.hi)) for j in range(self.n_sparse)]
             torch.cuda.synchronize()
+        self.graphs = {}
+        self._make_retriever()
+        self.setup_s = time.perf_counter() - t0
+
+    def _make_retriever(self):
+        from mfar_b200.dist import ShardedRetriever
+        from mfar_b200.modeling.retrieval import MultiFieldRetriever
+        ctx, a = self.ctx, self.ctx.args
+        self.graphs.clear()
         self.retr = MultiFieldRetriever(self.pc, self.layer, n_sparse=self.n_sparse, top_k=TOPK, doc_id_base=self.lo,
                                         impl=a.kernel, sparse_indices=self.bm25_fields, n_docs=self.hi - self.lo,
                                         device=ctx.device)
@@ -326,8 +346,39 @@ class Workload:
         # throughput mode of the timed loops: a step pushes its keys and merges the PREVIOUS step's, so no rank waits
         # for the slowest rank of the current step (results trail by one step; flush() returns the last one)
         self.piped = ShardedRetriever(self.retr, exchange=ctx.exchange, pipelined=ctx.pipelined)
-        self.setup_s = time.perf_counter() - t0
-        self.graphs = {}
+
+    def tune_boundaries(self, Q, rounds=4, steps=10, tol=0.006):
+        """Start-up, untimed: run the real sharded step, measure every rank's scoring-kernel time, move the shard
+        boundaries towards equal time (dist.rebalanced_boundaries), repeat.  Stops when the spread over the ranks is
+        below `tol`.  The history goes into the JSON line (config.sharding)."""
+        from mfar_b200 import _native as nv
+        from mfar_b200.dist import rebalanced_boundaries
+        ctx = self.ctx
+        if not self.margin:
+            return
+        pool = self.make_batches(Q, 2)
+        hist = []
+        for it in range(rounds + 1):
+            for i in range(3):
+                self.step(pool[i % 2], False)
+            ctx.barrier()
+            nv.check(nv.lib().mfar_profile_enable(1))
+            for i in range(steps):
+                self.step(pool[i % 2], False)
+            ctx.barrier()
+            km = self._collect_profile()
+            ts = ctx.per_rank(statistics.mean(km) if km else 0.0)
+            spread = (max(ts) - min(ts)) / max(min(ts), 1e-9)
+            hist.append({"kernel_ms": [round(x, 4) for x in ts], "spread": round(spread, 4),
+                         "cuts_minus_equal": [c - b for c, b in zip(self.cuts, self.base_cuts)]})
+            if spread < tol or it == rounds:
+                break
+            self.cuts = rebalanced_boundaries(self.cuts, ts, self.base_cuts, self.margin)
+            self.lo, self.hi = self.cuts[ctx.rank], self.cuts[ctx.rank + 1]
+            self.pc = self.pc_held.window(self.lo - self.held_lo, self.hi - self.lo)
+            self._make_retriever()
+        self.tuning = hist
+        del pool
 
     # ------------------------------------------------------------------ inputs
     def make_batches(self, Q, n_pool=4):
@@ -612,7 +663,7 @@ class Workload:
 
     def release(self):
         self.graphs.clear()
-        self.retr = self.sharded = self.pc = self.bm25_fields = None
+        self.retr = self.sharded = self.piped = self.pc = self.pc_held = self.bm25_fields = None
         gc.collect()
         torch.cuda.empty_cache()
 
@@ -622,8 +673,16 @@ def run_workload(ctx: Ctx, name, batches, steps, warmup, headline=False):
     a = ctx.args
     wl = Workload(ctx, name, a.docs if headline else 0)
     graph = bool(a.graph) or ctx.world > 1             # the sharded step is launch-sensitive: always replay it as a graph
+    if wl.margin:
+        t0 = time.perf_counter()
+        wl.tune_boundaries(batches[0])
+        wl.setup_s += time.perf_counter() - t0
     out = {"workload": name, "n_docs": wl.n_total, "n_dense": wl.n_dense, "n_sparse": wl.n_sparse,
            "shard_docs": wl.hi - wl.lo, "cuda_graph": graph, "setup_s": wl.setup_s, "batches": []}
+    if wl.tuning:
+        out["boundary_tuning"] = {"margin_docs": wl.margin, "rounds": wl.tuning,
+                                  "note": "untimed start-up: per-rank scoring-kernel ms of the real sharded step, "
+                                          "boundaries moved towards equal time within the resident margins"}
     for bi, Q in enumerate(batches):
         main = headline and bi == 0
         st, wu = (steps, warmup) if main else (max(5, steps // 2), 3)
@@ -685,8 +744,9 @@ def main():
                          "device from query tokens against HBM-resident BM25 postings (SURVEY 8f-3)")
     ap.add_argument("--graph", action="store_true",
                     help="N=1: replay the device-resident step as one CUDA graph (always on for N>1)")
-    ap.add_argument("--balance", default="auto", choices=["auto", "off"],
-                    help="N>1: size the doc ranges by each GPU's measured speed (auto) or equally (off)")
+    ap.add_argument("--balance", default="auto", choices=["auto", "static", "off"],
+                    help="N>1: auto = every rank holds a 6 %% margin of its neighbours' docs and the boundaries are tuned "
+                         "on the real step at start-up; static = one calibration run sizes the ranges; off = equal")
     ap.add_argument("--exchange-mode", default="complete", choices=["pipelined", "complete"],
                     help="N>1 timed loops: a step merges the previous step's keys (pipelined, no waiting for the slowest "
                          "rank of the step) or its own (complete)")
@@ -739,8 +799,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA sm_100 device (there is no CPU fallback for the product path)")
     ctx = Ctx(args)
-    if world > 1 and args.balance == "auto" and n_dense:
+    if world > 1 and args.balance == "static" and n_dense:
         ctx.calibrate(n_dense, Q, n_total // world)
+    if world > 1 and args.balance == "auto":
+        ctx.balance_note = "boundaries tuned at start-up on the measured per-rank step time (boundary_tuning)"
     config["sharding"] = f"doc-range x{world}, {ctx.balance_note}"
 
     extra = [int(x) for x in args.extra_batches.split(",") if x and int(x) != Q]
@@ -781,6 +843,7 @@ def main():
                                              "step's (results trail by one step)" if ctx.pipelined else ""),
             "clocks": main_rec["clocks"],
             "per_rank": main_rec.get("per_rank"),
+            "boundary_tuning": head.get("boundary_tuning"),
             "other_batches": [compact(r) for r in head["batches"][1:]],
             "other_workloads": [
                 o if "error" in o else

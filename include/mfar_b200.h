@@ -349,7 +349,9 @@ MFAR_API int mfar_last_launch_count(void);
 
 /* Per-launch device timing of the scoring kernel (the dominant kernel of a step), for the roofline
  * bench.py reports.  mfar_profile_enable(1) arms a ring of 256 CUDA event pairs recorded on the launch
- * stream around the scoring kernel of each subsequent mfar_score_topk call; mfar_profile_collect()
+ * stream around the scoring launches of each subsequent mfar_score_topk call (the main pass and, where threshold
+ * seeding applies, its one or two prefix passes with their small merge / seed kernels in between - together they read
+ * the corpus exactly once); mfar_profile_collect()
  * synchronises those events, writes their durations (ms) to a HOST array, returns how many, and
  * resets the ring.  Diagnostics only.  The ring is per host thread (thread-local state, events on the thread's current
  * device): arm and collect it from the thread that issues the calls; other threads / devices are unaffected.  It is off

@@ -32,7 +32,9 @@ static int check_arch() {
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-static size_t seed_scratch_bytes(int Q, int k) { return align_up(size_t(Q) * k * 8, 256) + align_up(size_t(Q) * 8, 256); }
+static size_t seed_scratch_bytes(int Q, int k) {      // two [Q,k] key buffers (prefix levels alternate) + [Q] seeds
+  return 2 * align_up(size_t(Q) * k * 8, 256) + align_up(size_t(Q) * 8, 256);
+}
 
 struct Geometry {
   int impl;       // resolved: MFAR_IMPL_SIMT, MFAR_IMPL_TCGEN05 or MFAR_IMPL_TCGEN05_QS
@@ -48,6 +50,10 @@ struct Geometry {
 constexpr int kImplRows = 100;    // internal: sparse-only scorers (no dense field) -> streaming top-k of the base rows
 
 constexpr int kQsMinBatch = 65;   // AUTO: batches above 64 queries take the query-stationary kernel
+
+#ifdef MFAR_DEBUG_SEED
+static const unsigned long long* g_debug_seed = nullptr;
+#endif
 
 static Geometry resolve_geometry(const ScoreArgs& a, int impl) {
   Geometry g{};
@@ -246,7 +252,7 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
                            sparse_rows_fusable(sp.dense, sp.dense_dtype, sp.dense_ld);
   const size_t ws_base = (n_sparse > 0 && !fuse_sparse) ? align_up(size_t(Q) * base_ld * 4, 256) : 0;
   const size_t ws_plan = (n_sparse > 0 && sp.kind == 3) ? bm25_plan_bytes(sp.n_entries) : 0;
-  // prefix keys [Q,k] + seed thresholds [Q] of the threshold-seeding pass (used when the caller's workspace has room)
+  // prefix keys 2 x [Q,k] + seed thresholds [Q] of the threshold-seeding passes (used when the caller's workspace has room)
   size_t ws_seed = seed_scratch_bytes(Q, k);
   if (workspace_bytes < ws_topk + ws_base + ws_plan) return MFAR_ERR_WORKSPACE;
   if (workspace_bytes < ws_topk + ws_base + ws_plan + ws_seed) ws_seed = 0;
@@ -296,41 +302,62 @@ static int score_topk_core(const void* corpus, int64_t n_docs, int corpus_fields
   const uint64_t* prefix_keys = nullptr;              // set when a scored prefix is left out of the main pass
   const bool seed = n_dense > 0 && (g.impl == MFAR_IMPL_TCGEN05 || g.impl == MFAR_IMPL_TCGEN05_QS) && Q >= 32 &&
                     a.n_tiles >= 16 * g.workers && ws_seed > 0;
-  if (seed) {
-    char* sb = static_cast<char*>(workspace) + ws_topk + ws_base + ws_plan;
-    uint64_t* pref_keys = reinterpret_cast<uint64_t*>(sb);
-    unsigned long long* seed_thr = reinterpret_cast<unsigned long long*>(sb + align_up(size_t(Q) * k * 8, 256));
-    ScoreArgs ap = a;
-    ap.n_tiles = g.workers;
-    ap.n_docs = int64_t(g.workers) * kTileDocs;
-    ap.gthr_seed = nullptr;
-    const Geometry gp = resolve_geometry(ap, g.impl);
-    if (g.impl == MFAR_IMPL_TCGEN05_QS) rc = launch_score_qs(ap, workspace, gp.workers, gp.q_tiles, gp.cg, st);
-    else rc = launch_score_tc(ap, workspace, gp.workers, gp.q_tiles, gp.q_pad, st);
-    if (rc) return rc;
-    TopkWorkspace wp = carve_workspace(workspace, gp.lists, gp.q_pad_total);
-    rc = launch_merge(wp.cand_keys, wp.cand_cnt, wp.cand_thr, gp.lists, gp.q_pad_total, kCandCap, Q, k, pref_keys, nullptr,
-                      nullptr, st);
-    if (rc) return rc;
-    if ((rc = launch_seed_from_keys(pref_keys, Q, k, seed_thr, st))) return rc;
-    a.gthr_seed = seed_thr;
-    t_last_launches += 4;                             // prefix scoring + merge + seed, and the copy into the main pass
-    // The prefix is not scored twice: the main pass starts behind it (every per-doc pointer advanced by the prefix's
-    // whole tiles) and the final merge takes the prefix's ranked top k as one more list.
-    const int64_t skip = ap.n_docs;
-    a.corpus = static_cast<const char*>(a.corpus) + size_t(g.workers) * a.corpus_fields * kTileDocs * a.dim * 2;
-    a.n_tiles -= g.workers;
-    a.n_docs -= skip;
-    a.doc_id_base += skip;
-    if (a.base) a.base += skip;
-    if (a.sparse) {
-      a.sparse = static_cast<const char*>(a.sparse) + size_t(skip) * (a.sparse_dtype == MFAR_F16 ? 2 : 4);
-      a.sparse_cols = a.sparse_ld - skip;
-    }
-    prefix_keys = pref_keys;
-  }
+  // the profiled interval covers every scoring launch of the call: the seeding passes are part of the corpus pass
   const bool prof = g_prof_on && g_prof_n < kProfRing;
   if (prof) MFAR_CUDA_OK(cudaEventRecord(g_prof_ev[g_prof_n][0], st));
+  if (seed) {
+    char* sb = static_cast<char*>(workspace) + ws_topk + ws_base + ws_plan;
+    const size_t keys_bytes = align_up(size_t(Q) * k * 8, 256);
+    uint64_t* pref_buf[2] = {reinterpret_cast<uint64_t*>(sb), reinterpret_cast<uint64_t*>(sb + keys_bytes)};
+    unsigned long long* seed_thr = reinterpret_cast<unsigned long long*>(sb + 2 * keys_bytes);
+    // Two prefix levels.  A: one tile per CTA, unseeded (a list takes its 128 docs without a compaction).  B: up to 31
+    // more tiles per CTA admitted against A's threshold (k-th best of workers*128 docs: ~2 % pass at Q=512 where a
+    // query has 37 lists, 0.5 % at Q<=64) - still no list fills - after which the seed is the k-th best of up to
+    // 32*workers*128 docs (0.07 % / 0.02 %).  Measured with the TRUE k-th keys as the seed (tools/seed_potential.py): a
+    // 1.25M-doc x 8-field shard at Q=512 runs 6.26 ms with A alone and 5.47 ms with a perfect seed, 5.49 ms with the
+    // k-th keys of a 150k-doc prefix - the lists of a mid-size shard never fill, so their thresholds never tighten
+    // by themselves and every weakly filtered doc costs the epilogue its slow path.
+    // B only where A's threshold would still let a list fill during the main pass (expected admissions per list
+    // n_docs * k / (docs of A) / lists above ~96): a 700k-doc shard at Q=64 has 148 lists per query and ~25 admissions
+    // per list after A alone - there B's extra launch and merge cost 2 %.
+    const int per_worker = a.n_tiles / g.workers;
+    const double after_a = double(a.n_docs) * k / (double(g.workers) * kTileDocs) / double(g.lists);
+    int level_tiles[2] = {1, std::min(31, per_worker / 4 - 1)};
+    const int n_levels = (level_tiles[1] >= 3 && after_a > 96.0) ? 2 : 1;
+    for (int lv = 0; lv < n_levels; ++lv) {
+      ScoreArgs ap = a;                                 // `a` already starts behind the previous level
+      ap.n_tiles = g.workers * level_tiles[lv];
+      ap.n_docs = int64_t(ap.n_tiles) * kTileDocs;
+      const Geometry gp = resolve_geometry(ap, g.impl);
+      if (g.impl == MFAR_IMPL_TCGEN05_QS) rc = launch_score_qs(ap, workspace, gp.workers, gp.q_tiles, gp.cg, st);
+      else rc = launch_score_tc(ap, workspace, gp.workers, gp.q_tiles, gp.q_pad, st);
+      if (rc) return rc;
+      TopkWorkspace wp = carve_workspace(workspace, gp.lists, gp.q_pad_total);
+      uint64_t* pref_keys = pref_buf[lv & 1];           // ranked top k of everything scored so far
+      rc = launch_merge(wp.cand_keys, wp.cand_cnt, wp.cand_thr, gp.lists, gp.q_pad_total, kCandCap, Q, k, pref_keys,
+                        nullptr, nullptr, st, prefix_keys, prefix_keys ? k : 0);
+      if (rc) return rc;
+      if ((rc = launch_seed_from_keys(pref_keys, Q, k, seed_thr, st))) return rc;
+#ifdef MFAR_DEBUG_SEED   // experiment builds only: replace the prefix seed by thresholds the caller supplies
+      if (g_debug_seed) MFAR_CUDA_OK(cudaMemcpyAsync(seed_thr, g_debug_seed, size_t(Q) * 8, cudaMemcpyDeviceToDevice, st));
+#endif
+      t_last_launches += 4;                             // prefix scoring + merge + seed, and the copy into the next pass
+      // A prefix is not scored twice: the next pass starts behind it (every per-doc pointer advanced by the prefix's
+      // whole tiles) and the next merge takes the prefix's ranked top k as one more list.
+      const int64_t skip = ap.n_docs;
+      a.corpus = static_cast<const char*>(a.corpus) + size_t(ap.n_tiles) * a.corpus_fields * kTileDocs * a.dim * 2;
+      a.n_tiles -= ap.n_tiles;
+      a.n_docs -= skip;
+      a.doc_id_base += skip;
+      if (a.base) a.base += skip;
+      if (a.sparse) {
+        a.sparse = static_cast<const char*>(a.sparse) + size_t(skip) * (a.sparse_dtype == MFAR_F16 ? 2 : 4);
+        a.sparse_cols = (a.sparse_cols ? a.sparse_cols : a.sparse_ld) - skip;
+      }
+      a.gthr_seed = seed_thr;
+      prefix_keys = pref_keys;
+    }
+  }
   if (g.impl == kImplRows)
     rc = launch_topk_rows(a, workspace, g.workers, g.seg_docs, st);
   else if (g.impl == MFAR_IMPL_TCGEN05_QS)
@@ -755,6 +782,10 @@ int mfar_mixture_bwd(const float* x, const float* q_emb, const float* W, const f
 }
 
 int mfar_last_launch_count(void) { return t_last_launches; }
+
+#ifdef MFAR_DEBUG_SEED
+MFAR_API void mfar_debug_set_seed(const void* seed) { g_debug_seed = static_cast<const unsigned long long*>(seed); }
+#endif
 
 int mfar_profile_enable(int on) {
   if (on) {

@@ -39,6 +39,41 @@ def weighted_shard_ranges(n_docs: int, weights: Sequence[float], align: int = 12
     return [(cuts[i], cuts[i + 1]) for i in range(len(w))]
 
 
+def held_ranges(cuts: Sequence[int], margin: int, n_docs: int) -> List[Tuple[int, int]]:
+    """Doc ranges each rank keeps RESIDENT when its active range may move by up to ``margin`` docs at either end:
+    rank r holds ``[cuts[r] - margin, cuts[r+1] + margin)`` clipped to the corpus."""
+    return [(max(0, cuts[r] - margin), min(n_docs, cuts[r + 1] + margin)) for r in range(len(cuts) - 1)]
+
+
+def rebalanced_boundaries(cuts: Sequence[int], step_ms: Sequence[float], base_cuts: Sequence[int], margin: int,
+                          align: int = 128, damping: float = 0.8) -> List[int]:
+    """One step of shard-boundary tuning.  ``cuts`` = current boundaries (``R+1`` doc ids, ``cuts[0] = 0``,
+    ``cuts[R] = n_docs``), ``step_ms[r]`` = the time rank r just needed for its range.  Ranges are resized towards
+    sizes proportional to the measured docs/ms (``damping`` of the way), boundaries rounded to ``align`` docs (a window
+    of a tile-major corpus starts on a tile) and kept within ``margin`` docs of ``base_cuts`` - the ranges the ranks
+    hold resident (``held_ranges``), so moving a boundary is a pointer offset on both sides, never a copy.
+
+    Why: the job runs at the pace of its slowest rank, and the GPUs of a node differ by a few per cent under the power
+    cap - persistently enough that a calibration on another kernel size or moment mis-predicts it; the real step,
+    measured and corrected a few times at start-up, does not."""
+    R = len(cuts) - 1
+    n_docs = cuts[-1]
+    sizes = [cuts[r + 1] - cuts[r] for r in range(R)]
+    speed = [sizes[r] / max(float(step_ms[r]), 1e-9) for r in range(R)]
+    total = sum(speed)
+    target = [n_docs * v / total for v in speed]
+    new_sizes = [(1.0 - damping) * sizes[r] + damping * target[r] for r in range(R)]
+    out, acc = [0], 0.0
+    for r in range(R - 1):
+        acc += new_sizes[r]
+        c = int(round(acc / align)) * align
+        c = min(max(c, base_cuts[r + 1] - margin), base_cuts[r + 1] + margin)     # stay inside what both sides hold
+        c = min(max(c, out[-1] + align), n_docs - align * (R - 1 - r))            # ranges stay non-empty and ordered
+        out.append(c)
+    out.append(n_docs)
+    return out
+
+
 # ---- host-side mirror of the device key packing (csrc/common.cuh) - used by tests and debugging
 def encode_keys(scores: np.ndarray, ids: np.ndarray) -> np.ndarray:
     u = np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32).astype(np.uint64)

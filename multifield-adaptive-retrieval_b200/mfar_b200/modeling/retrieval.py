@@ -18,6 +18,7 @@ from .. import _native as nv
 from ..data.trec import QRes
 from .weighting import LinearWeights
 
+TILE_DOCS = nv.TILE_DOCS
 KCHUNK = 64   # the tensor-core path consumes K in 64-element (128-byte) chunks
 
 
@@ -85,6 +86,22 @@ class PackedCorpus:
                           normalize: bool = False) -> "PackedCorpus":
         """vectors_dict: field key -> MemoryMapDict, as returned by ``read_and_create_indices``."""
         return cls.from_fields([vectors_dict[k].file for k in dense_keys], device, normalize)
+
+    def window(self, doc_begin: int, n_docs: int) -> "PackedCorpus":
+        """Docs [doc_begin, doc_begin + n_docs) as a corpus of their own WITHOUT a copy (the layout is tile-major, so a
+        window that starts on a 128-doc tile boundary is a pointer offset).  A shard that holds a margin of its neighbours'
+        docs can move its boundaries this way (``dist.rebalanced_boundaries``)."""
+        if doc_begin % TILE_DOCS or doc_begin < 0 or n_docs <= 0 or doc_begin + n_docs > self.n_docs:
+            raise ValueError(f"window [{doc_begin}, {doc_begin + n_docs}) must start on a {TILE_DOCS}-doc tile boundary "
+                             f"inside the corpus of {self.n_docs} docs")
+        view = PackedCorpus.__new__(PackedCorpus)
+        view.device, view.n_fields, view.dim, view.dim_pad = self.device, self.n_fields, self.dim, self.dim_pad
+        view.normalize, view.n_docs = self.normalize, int(n_docs)
+        per_tile = self.n_fields * TILE_DOCS * self.dim_pad
+        n_el = nv.lib().mfar_corpus_packed_elems(view.n_docs, self.n_fields, self.dim_pad)
+        first = (doc_begin // TILE_DOCS) * per_tile
+        view.data = self.data[first:first + n_el]
+        return view
 
     def unpack_field(self, field: int, row_begin: int = 0, n_rows: Optional[int] = None) -> torch.Tensor:
         n_rows = self.n_docs - row_begin if n_rows is None else n_rows

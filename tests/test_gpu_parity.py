@@ -400,6 +400,40 @@ def test_virtual_shards_merge_equals_single_shard(impl):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
+def test_corpus_windows_with_moved_boundaries_equal_the_unsharded_search(impl):
+    """Tunable shard boundaries (dist.held_ranges / rebalanced_boundaries, PackedCorpus.window): every virtual rank packs
+    its range plus a margin of its neighbours' docs, searches a zero-copy WINDOW of it, the boundaries move, and the
+    merged result stays bit-identical to the unsharded search - before and after the move."""
+    MultiFieldRetriever, PackedCorpus, LinearWeights = _mods()
+    from mfar_b200.dist import held_ranges, merge_keys, rebalanced_boundaries, weighted_shard_ranges
+    N, R, k, margin = 6000, 3, 100, 384
+    fields, q, _, W = synth(43, N, 256, 2, 0, 40, True)
+    full = build(fields, W, True, 0, k, impl=impl)
+    s0, i0, _ = full.search(q.to(DEV), q.to(DEV), None, return_keys=True)
+    base = [r[0] for r in weighted_shard_ranges(N, [1.0] * R)] + [N]
+    held = held_ranges(base, margin, N)
+    packed = [PackedCorpus.from_fields([f[lo:hi] for f in fields], DEV) for lo, hi in held]
+    layer = full.mixture
+    cuts = list(base)
+    for step_ms in (None, [1.0, 1.3, 0.9], [1.2, 1.0, 1.0]):
+        if step_ms is not None:
+            cuts = rebalanced_boundaries(cuts, step_ms, base, margin)
+            assert cuts != base and all(abs(c - b) <= margin and c % 128 == 0 for c, b in zip(cuts[1:-1], base[1:-1]))
+        keys = []
+        for r in range(R):
+            lo, hi = cuts[r], cuts[r + 1]
+            win = packed[r].window(lo - held[r][0], hi - lo)
+            assert win.data.data_ptr() == packed[r].data.data_ptr() + \
+                (lo - held[r][0]) // 128 * 2 * 128 * win.dim_pad * 2          # a pointer offset, not a copy
+            sh = MultiFieldRetriever(win, layer, top_k=k, doc_id_base=lo, impl=impl, n_docs=hi - lo, device=DEV)
+            keys.append(sh.search(q.to(DEV), q.to(DEV), None, return_keys=True)[2])
+        s, i = merge_keys(torch.stack(keys), k)
+        assert torch.equal(i, i0) and torch.equal(s, s0), cuts
+    with pytest.raises(ValueError):
+        packed[0].window(64, 100)                                              # not on a tile boundary
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 def test_sparse_coo_input_equals_dense_input_and_oracle(impl, tmp_path):
     """Sparse scores given in the reference's precomputed-BM25 file layout (int32 (qid, doc) pairs + f16 values per
     field, precompute_bm25s_scores.py:21-30) vs the same scores as a dense [Q,Fs,N] tensor vs the oracle; a sharded

@@ -315,6 +315,32 @@ def test_weighted_shard_ranges_cover_the_corpus_and_follow_the_weights():
     assert z[1][1] - z[1][0] <= 1 and z[-1][1] == 1000
 
 
+def test_rebalanced_boundaries_converge_to_equal_time_inside_the_margins():
+    from mfar_b200.dist import held_ranges, rebalanced_boundaries, weighted_shard_ranges
+    n, R = 10_000_000, 8
+    base = [r[0] for r in weighted_shard_ranges(n, [1.0] * R)] + [n]
+    margin = 75_008
+    held = held_ranges(base, margin, n)
+    assert held[0][0] == 0 and held[-1][1] == n and all(lo % 128 == 0 for lo, _ in held)
+    assert all(h[0] == b - margin for h, b in zip(held[1:], base[1:]))
+    docs_per_ms = [201.6, 198.4, 195.3, 201.6, 186.6, 201.6, 195.3, 201.6]    # what each "GPU" really does
+    cuts = list(base)
+    for _ in range(4):
+        t = [(cuts[r + 1] - cuts[r]) / docs_per_ms[r] for r in range(R)]
+        cuts = rebalanced_boundaries(cuts, t, base, margin)
+        assert cuts[0] == 0 and cuts[-1] == n and all(a < b for a, b in zip(cuts, cuts[1:]))
+        assert all(c % 128 == 0 and abs(c - b) <= margin for c, b in zip(cuts[1:-1], base[1:-1]))
+        for r in range(R):                                   # the active range stays inside what the rank holds
+            assert held[r][0] <= cuts[r] and cuts[r + 1] <= held[r][1]
+    t = [(cuts[r + 1] - cuts[r]) / docs_per_ms[r] for r in range(R)]
+    assert (max(t) - min(t)) / min(t) < 1e-3
+    # a rank far slower than the margin allows: boundaries stop at the margin instead of leaving the resident range
+    slow = rebalanced_boundaries(list(base), [1.0, 3.0] + [1.0] * 6, base, margin, damping=1.0)
+    assert slow[1] == base[1] + margin and slow[2] >= base[2] - margin
+    # equal times leave equal boundaries alone
+    assert rebalanced_boundaries(list(base), [5.0] * R, base, margin) == base
+
+
 def test_sparse_score_store_matches_the_reference_loader_golden(tmp_path):
     """tests/golden/loader/sparse_scores.npz was produced by the reference's own ``read_sparse_scores`` +
     ``score_batch_with_cache`` (oracle/make_golden_sparse_scores.py): same [Q,C] matrices (missing -> 0, the later of
