@@ -744,9 +744,13 @@ def main():
                          "device from query tokens against HBM-resident BM25 postings (SURVEY 8f-3)")
     ap.add_argument("--graph", action="store_true",
                     help="N=1: replay the device-resident step as one CUDA graph (always on for N>1)")
-    ap.add_argument("--balance", default="auto", choices=["auto", "static", "off"],
-                    help="N>1: auto = every rank holds a 6 %% margin of its neighbours' docs and the boundaries are tuned "
-                         "on the real step at start-up; static = one calibration run sizes the ranges; off = equal")
+    ap.add_argument("--balance", default="off", choices=["auto", "static", "off"],
+                    help="N>1: off = equal doc ranges (default: under the node's power cap the per-GPU speed FLUCTUATES "
+                         "by several per cent from one 50 ms window to the next rather than differing persistently, and "
+                         "both tuners below chase that noise - measured 79.5k q/s tuned vs 81.0k equal at N=8, "
+                         "profiles/r2_bench_n8_tuned_vs_equal.md); auto = every rank holds a 6 %% margin of its "
+                         "neighbours' docs and the boundaries are tuned on the real step at start-up; static = one "
+                         "calibration run sizes the ranges")
     ap.add_argument("--exchange-mode", default="complete", choices=["pipelined", "complete"],
                     help="N>1 timed loops: a step merges the previous step's keys (pipelined, no waiting for the slowest "
                          "rank of the step) or its own (complete)")
