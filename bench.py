@@ -563,6 +563,10 @@ class Workload:
                      "traffic_source": "ncu --set full capture of this kernel at this shape, profiles/ncu_traffic.json "
                                        "(a profiler pass, not re-measured in this run)" if traffic else None,
                      "kernel": kname, "kernel_ms": k_ms,
+                     "kernel_ms_is": "mean CUDA-event time, on the launch stream, around ALL scoring launches of a call: "
+                                     "the main pass and, where threshold seeding applies (Q >= 32, >= 16 tiles per CTA), "
+                                     "its one or two prefix passes of the same kernel with their merge / seed kernels in "
+                                     "between - together they read the corpus once (the algorithmic bytes / flops below)",
                      "kernel_share_of_step": k_ms * steps / ms_total if ms_total else None,
                      "algorithmic_bytes_per_launch": a_bytes, "algorithmic_flops_per_launch": a_flops,
                      "peak_source": peaks["source"] + (" copy bandwidth" if hbm_bound else
