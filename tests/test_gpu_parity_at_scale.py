@@ -30,12 +30,16 @@ CASES = {
     "c5_shard_of_8": (1_250_000, 8, 0, 3_750_000, True, None, 104, 512),      # rank 3's doc range of the 8-GPU run
     "c5_single": (10_000_000, 1, 0, 0, False, None, 105, 512),
     "c5_all": (10_000_000, 8, 0, 0, True, None, 1234, 512),
+    # threshold-seeding edges (csrc/capi.cu): a ragged last tile, doc ids near 2^32, fp32 sparse rows behind the
+    # advanced pointers; Q=40 seeds with one prefix level (doc-stationary), Q=300 with two (query-stationary, 37 lists)
+    "c6_seed_edges": (330_001, 2, 2, 3_900_000_000, True, 1, 106, 300, torch.float32),
 }
 
 # (case, batch, impl).  impl "tcgen05" = doc-stationary kernel, "tcgen05_qs" = query-stationary, "auto" = what ships.
 RUNS = []
 for _c, _batches in (("c2_prime_hybrid", (1, 64, 200)), ("c3_mag", (1, 512)), ("c4_amazon_hybrid", (64, 512)),
-                     ("c5_shard_of_8", (1, 512)), ("c5_single", (1, 64, 128, 512)), ("c5_all", (1, 64, 512))):
+                     ("c5_shard_of_8", (1, 512)), ("c5_single", (1, 64, 128, 512)), ("c5_all", (1, 64, 512)),
+                     ("c6_seed_edges", (40, 300))):
     for _b in _batches:
         for _impl in ("tcgen05", "tcgen05_qs", "auto"):
             RUNS.append((_c, _b, _impl))
@@ -49,10 +53,10 @@ def _free():
     torch.cuda.empty_cache()
 
 
-def _make_sparse(Q, Fs, n, seed):
+def _make_sparse(Q, Fs, n, seed, dtype=torch.float16):
     from mfar_b200 import synth as S
     ld = (n + 63) // 64 * 64                       # 128-byte rows: gathered inside the scoring epilogue
-    out = torch.zeros((Q, Fs, ld), dtype=torch.float16, device=DEV)
+    out = torch.zeros((Q, Fs, ld), dtype=dtype, device=DEV)
     for q0 in range(0, Q, 32):                     # bounded temporaries (fp32 [32,Fs,N] x 4)
         q1 = min(Q, q0 + 32)
         out[q0:q1, :, :n] = S.make_sparse(q1 - q0, Fs, n, seed + q0, DEV)
@@ -68,7 +72,8 @@ def _case(name):
     from mfar_b200 import synth as S
     from mfar_b200.modeling.retrieval import MultiFieldRetriever, PackedCorpus
     from mfar_b200.modeling.weighting import LinearWeights
-    n, Fd, Fs, base, qc, masked, seed, Qmax = CASES[name]
+    n, Fd, Fs, base, qc, masked, seed, Qmax = CASES[name][:8]
+    sp_dtype = CASES[name][8] if len(CASES[name]) > 8 else torch.float16
     need = n * Fd * D * 2 + Qmax * Fs * n * 2 + 8e9
     free, _ = torch.cuda.mem_get_info()
     if free < need:
@@ -82,7 +87,7 @@ def _case(name):
     with torch.no_grad():
         layer.weight.copy_(S.make_mixture(D, F, seed + 2, query_cond=qc))
     layer = layer.to(DEV)
-    sp = _make_sparse(Qmax, Fs, n, seed + 3) if Fs else None
+    sp = _make_sparse(Qmax, Fs, n, seed + 3, sp_dtype) if Fs else None
     r = MultiFieldRetriever(pc, layer, n_sparse=Fs, top_k=K, doc_id_base=base)
     if masked is not None:
         r.mask_field([masked])
@@ -122,11 +127,7 @@ def test_c5_all_shards_and_host_call_equal_unsharded():
     cut = 128 * 40_000
     parts = []
     for lo, hi in ((0, cut), (cut, pc.n_docs)):
-        view = PackedCorpus.__new__(PackedCorpus)
-        view.device, view.n_docs, view.n_fields, view.dim, view.dim_pad, view.normalize = (
-            pc.device, hi - lo, pc.n_fields, pc.dim, pc.dim_pad, False)
-        view.data = pc.data[(lo // 128) * pc.n_fields * 128 * pc.dim_pad:]
-        sh = MultiFieldRetriever(view, r.mixture, top_k=K, doc_id_base=lo)
+        sh = MultiFieldRetriever(pc.window(lo, hi - lo), r.mixture, top_k=K, doc_id_base=lo)
         parts.append(sh.search(q, q.float(), return_keys=True)[2])
     s_m, i_m = merge_keys(torch.stack(parts), K)
     assert torch.equal(i_m, i_c) and torch.equal(s_m, s_c)
