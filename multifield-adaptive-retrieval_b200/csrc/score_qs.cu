@@ -197,6 +197,7 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
   uint8_t* smem_b = smem;
   uint8_t* smem_sp = smem_b + size_t(p.stages) * kStageBytes;                          // [sp_slots][16 KB], 1024-aligned
   const int sp_slots = SP ? p.sp_slots : 0;
+  const int sp_ring = SP ? p.sp_slots : 1;           // ring arithmetic below (1: well-defined in the dense-only instantiations)
   float* w_s = reinterpret_cast<float*>(smem_sp + size_t(sp_slots) * kSpSlotBytes);    // [n_dense (+ n_sparse)][128]
   const int n_w = p.n_dense + (SP ? p.n_sparse : 0);   // weight rows kept in shared memory
   uint64_t* bars = reinterpret_cast<uint64_t*>(w_s + size_t(n_w) * kQsQ);
@@ -363,8 +364,8 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
           const int h = ES == 2 ? b : a, e = ES == 2 ? a : b;
           const int64_t doc0 = tile_doc0 + h * kQsDocs;
           if (doc0 < p.n_docs) {                     // (the epilogue skips a half-tile past the last doc too)
-            const int slot = seq % sp_slots;
-            mbar_wait(&sempty_bar[slot], ((seq / sp_slots) & 1) ^ 1, err, 16);
+            const int slot = seq % sp_ring;
+            mbar_wait(&sempty_bar[slot], ((seq / sp_ring) & 1) ^ 1, err, 16);
             if (elect_one()) {
               mbar_expect_tx(&sfull_bar[slot], kSpSlotBytes);
               const int j = p.sparse_f16 ? e : (e >> 1);
@@ -451,8 +452,8 @@ score_qs_kernel(const __grid_constant__ CUtensorMap map_b, const __grid_constant
     const int sp_elems = SP ? p.n_sparse * (p.sparse_f16 ? 1 : 2) : 0;
     int sp_seq = (ES == 2) ? eset : 0;               // ES = 2: set s consumes elements s, s + 2, ...
     auto sp_step = [&](int sp_e, float (&acc_)[kQsDocs]) {
-      const int slot = sp_seq % sp_slots;
-      mbar_wait(&sfull_bar[slot], (sp_seq / sp_slots) & 1, err, 17);
+      const int slot = sp_seq % sp_ring;
+      mbar_wait(&sfull_bar[slot], (sp_seq / sp_ring) & 1, err, 17);
       const int j = p.sparse_f16 ? sp_e : (sp_e >> 1);
       qs_sparse_consume(smem_sp + size_t(slot) * kSpSlotBytes, qloc, p.sparse_f16 != 0, sp_e,
                         w_s[(p.n_dense + j) * kQsQ + qloc], acc_);
